@@ -1,0 +1,185 @@
+/*
+ * dmf.h — C ABI of the B200-native dense monocular depth filter ("dmf").
+ *
+ * This is the drop-in boundary for ONE path of luigifreda/slamplay: the per-pixel
+ * `update()` loop of dense_mapping/test_monocular_mapping.cpp.  The reference has no
+ * FFI/plugin layer for this path; its boundary is the free function
+ *
+ *     void update(const Mat &ref, const Mat &curr, const SE3d &T_C_R,
+ *                 Mat &depth, Mat &depth_cov2);
+ *     (declared dense_mapping/test_monocular_mapping.cpp:107-112, defined :355-393,
+ *      single call site :291)
+ *
+ * Every entry point below names the reference lines it replaces.  The C++ shim
+ * `slamplay_b200/cpp/dense_mono_update.hpp` re-exposes exactly the reference
+ * signature on cv::Mat / Sophus::SE3d (or layout-compatible stand-ins) and forwards
+ * here; `slamplay_b200/depth_filter.py` is the ctypes binding used by tests/bench.
+ *
+ * Plain pointers and sizes only; no torch / OpenCV / Eigen types cross this ABI.
+ * All functions return 0 on success or a negative dmf_status; the message is
+ * available from dmf_last_error().  There is NO CPU fallback: every compute entry
+ * point fails with DMF_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef DMF_H_
+#define DMF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMF_ABI_VERSION 1
+
+typedef enum dmf_status {
+    DMF_OK = 0,
+    DMF_ERR_INVALID = -1,   /* bad argument (null pointer, size mismatch, bad params) */
+    DMF_ERR_CUDA = -2,      /* CUDA runtime error / no usable device */
+    DMF_ERR_STATE = -3,     /* call order violation (e.g. update before set_reference) */
+    DMF_ERR_NOMEM = -4
+} dmf_status;
+
+/*
+ * Runtime form of the file-scope constants of the reference
+ * (dense_mapping/test_monocular_mapping.cpp:72-89) and of the literals used inside
+ * epipolarSearch (:412-414 n_sigma/min_depth, :422 max_half_len, :432 step,
+ * :443 ncc_thresh).  dmf_default_params() fills in the reference values.
+ */
+typedef struct dmf_params {
+    int32_t width;          /* :73  */
+    int32_t height;         /* :74  */
+    int32_t border;         /* :72  (20) */
+    int32_t ncc_half;       /* :79  ncc_window_size (3); only 3 is supported by the kernels */
+    double fx, fy, cx, cy;  /* :75-78 (float literals widened to double) */
+    double step;            /* :432 0.7 */
+    double max_half_len;    /* :422 100 */
+    double min_depth;       /* :414 0.1 */
+    double n_sigma;         /* :412 3 */
+    double ncc_thresh;      /* :443 (double)0.85f */
+    double min_cov;         /* :86  0.01*0.01   (inverse-depth variant :82  1e-4) */
+    double max_cov;         /* :87  10          (inverse-depth variant :83  1)    */
+    int32_t inverse_depth;  /* :63  USE_INVERSE_DEPTH_FOR_FILTERING (0 in the reference build) */
+    int32_t reserved;
+} dmf_params;
+
+/* Work counters: they define the algorithmic work of a run. */
+typedef struct dmf_counters {
+    uint64_t frames;      /* update() calls since last reset */
+    uint64_t interior;    /* pixels visited by the loops :357,:363 (band-local) */
+    uint64_t active;      /* pixels passing the gate :366 */
+    uint64_t ncc_evals;   /* NCC() calls :437 */
+    uint64_t accepted;    /* epipolarSearch() returning true :443-446 */
+} dmf_counters;
+
+typedef struct dmf_ctx dmf_ctx;
+
+/* Library/ABI version and build info ("sm_100a", compile date). Never fails. */
+int dmf_abi_version(void);
+const char *dmf_build_info(void);
+
+/* Last error message of `ctx`, or of the calling thread when ctx == NULL. */
+const char *dmf_last_error(const dmf_ctx *ctx);
+
+/*
+ * Reference constants :72-89 for a width x height image.  For 640x480 the
+ * intrinsics are exactly the reference's float literals (fx = (double)481.2f, ...);
+ * for other sizes they are scaled by width/640 with the principal point at the image
+ * centre (SURVEY.md §8d synthetic inputs).  inverse_depth selects the :82-83 thresholds.
+ */
+int dmf_default_params(dmf_params *p, int width, int height, int inverse_depth);
+
+/*
+ * Create a filter context on CUDA device `device` that owns interior rows
+ * [row_begin, row_end) of the depth / depth_cov2 maps (clamped to
+ * [border, height-border), loop bounds of :357).  Pass 0, height for a single-GPU
+ * context.  Allocates the state maps (:277-278) in HBM; they stay resident until
+ * dmf_destroy().
+ */
+int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out);
+void dmf_destroy(dmf_ctx *ctx);
+
+/* Geometry of the context. */
+int dmf_get_params(const dmf_ctx *ctx, dmf_params *out);
+int dmf_get_band(const dmf_ctx *ctx, int *row_begin, int *row_end);
+
+/*
+ * Set the reference image (`ref` argument of update(), :108; CV_8UC1, `step` bytes
+ * per row as cv::Mat::step).  Also runs the once-per-reference precompute of the
+ * reference-patch mean and centred energy (ref half of NCC(), :458-459,468,476).
+ * _host: pageable or pinned host memory; _device: device memory on ctx's device.
+ */
+int dmf_set_reference(dmf_ctx *ctx, const uint8_t *ref_host, size_t step);
+int dmf_set_reference_device(dmf_ctx *ctx, const uint8_t *ref_dev, size_t step);
+
+/*
+ * State maps `depth`, `depth_cov2` (CV_64F, :277-278).  Host pointers address the
+ * FULL image (row 0), `step` in bytes; only the context's band rows are transferred.
+ * dmf_fill_state is the device-side equivalent of Mat(h,w,CV_64F,init) (:277-278).
+ * dmf_download_state synchronises the context stream first (update() results are
+ * visible to the caller on return, :292-300).
+ */
+int dmf_fill_state(dmf_ctx *ctx, double init_depth, double init_cov2);
+int dmf_upload_state(dmf_ctx *ctx, const double *depth, size_t depth_step,
+                     const double *cov2, size_t cov2_step);
+int dmf_download_state(dmf_ctx *ctx, double *depth, size_t depth_step,
+                       double *cov2, size_t cov2_step);
+
+/*
+ * One update() call (:355-393) against the current frame `curr` (CV_8UC1) with
+ * T_C_R given as Sophus stores it: unit quaternion (x,y,z,w) + translation.
+ * Asynchronous on the context stream; the host frame is consumed (copied to a
+ * device staging buffer) before return unless it is pinned memory obtained from
+ * dmf_alloc_pinned(), in which case it must stay untouched until dmf_sync().
+ * _device: frame already in HBM on ctx's device (e.g. received by NCCL broadcast);
+ * the launch is ordered after everything previously enqueued on `wait_stream`
+ * (a cudaStream_t, may be NULL).
+ */
+int dmf_update(dmf_ctx *ctx, const uint8_t *curr_host, size_t step,
+               const double q_xyzw[4], const double t_xyz[3]);
+int dmf_update_device(dmf_ctx *ctx, const uint8_t *curr_dev, size_t step,
+                      const double q_xyzw[4], const double t_xyz[3], void *wait_stream);
+
+int dmf_sync(dmf_ctx *ctx);
+
+/* Work counters accumulated on the device; `reset` != 0 clears them after reading. Syncs. */
+int dmf_read_counters(dmf_ctx *ctx, dmf_counters *out, int reset);
+
+/*
+ * Per-pixel decision flags of the LAST update (parity metric P2):
+ * bit0 = passed the gate :366, bit1 = epipolarSearch accepted :443.  Disabled by
+ * default; enabling costs one byte store per interior pixel per frame.
+ */
+int dmf_enable_flags(dmf_ctx *ctx, int enable);
+int dmf_download_flags(dmf_ctx *ctx, uint8_t *flags_host, size_t step);
+
+/*
+ * Raw device pointers for the multi-GPU gather (row-band sharding):
+ * full-image pitch-linear maps, `pitch` bytes per row; rows outside the band hold the
+ * last uploaded / filled values.  `stream` is the context's cudaStream_t.
+ */
+int dmf_device_state(dmf_ctx *ctx, double **depth_dev, double **cov2_dev, size_t *pitch);
+int dmf_stream(dmf_ctx *ctx, void **stream);
+
+/* Pinned host memory helpers for zero-staging dmf_update() calls. */
+int dmf_alloc_pinned(void **ptr, size_t bytes);
+int dmf_free_pinned(void *ptr);
+
+/*
+ * "Next" rows — consumers of the maps, evaluated on the device so a
+ * caller need not download 16*W*H bytes per frame.
+ *
+ * dmf_evaluate_depth: evaludateDepth() (:569-590) over the context's band:
+ *   sum of squared (truth - estimate) over interior pixels with variance < max_variance,
+ *   and their count.  RMS = sqrt(sum_sq / count).  truth is a full-image host map.
+ * dmf_variance_mask: getMaskFromVariance() (:199-204): mask = variance > max_variance ? 0 : 255
+ *   (cv::threshold THRESH_BINARY_INV then convertTo CV_8U), band rows only.
+ */
+int dmf_set_truth(dmf_ctx *ctx, const double *truth_host, size_t step);
+int dmf_evaluate_depth(dmf_ctx *ctx, double max_variance, double *sum_sq, uint64_t *count);
+int dmf_variance_mask(dmf_ctx *ctx, double max_variance, uint8_t *mask_host, size_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMF_H_ */

@@ -1,0 +1,479 @@
+// dmf_api.cu — C ABI (include/dmf.h) over the sm_100a kernels in dmf_kernels.cuh.
+// Host-side logic only: context, HBM-resident state, double-buffered frame upload,
+// pose inversion (Sophus SE3::inverse, used at ref:491), launches.
+#include "../../include/dmf.h"
+#include "dmf_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct dmf_ctx_impl {
+    dmf_params prm{};
+    int device = 0;
+    int row_begin = 0, row_end = 0;  // interior rows owned (clamped)
+    int band_lo = 0, band_hi = 0;    // rows transferred by upload/download (as requested by the caller)
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // images
+    uint8_t *d_ref = nullptr;
+    uint8_t *d_curr[2] = {nullptr, nullptr};
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of buffer b finished (copy stream)
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // kernel that read buffer b finished (compute stream)
+    cudaEvent_t ev_ext = nullptr;
+    int img_pitch = 0;  // bytes, multiple of 16
+    int2 *d_refstat = nullptr;
+    double *d_depth = nullptr, *d_cov2 = nullptr, *d_truth = nullptr;
+    uint8_t *d_flags = nullptr, *d_mask = nullptr;
+    unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
+    double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
+    bool have_ref = false, flags_on = false, have_truth = false;
+    unsigned long long frames = 0;
+    unsigned long long frame_idx = 0;
+    std::string err;
+};
+
+int fail(dmf_ctx_impl *c, int code, const std::string &msg) {
+    g_err = msg;
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(c, DMF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+struct Q4 { double x, y, z, w; };
+void rot(const Q4 &q, const double v[3], double out[3]) {  // Eigen _transformVector
+    double ux = q.y * v[2] - q.z * v[1], uy = q.z * v[0] - q.x * v[2], uz = q.x * v[1] - q.y * v[0];
+    ux += ux; uy += uy; uz += uz;
+    out[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+    out[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+    out[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+
+// Sophus SE3::inverse(): invR = SO3(conj(q)) (constructor normalises), t' = invR * (t * -1)
+void se3_inverse(const double q[4], const double t[3], double qi[4], double ti[3]) {
+    Q4 c{-q[0], -q[1], -q[2], q[3]};
+    double n = std::sqrt((c.x * c.x + c.z * c.z) + (c.y * c.y + c.w * c.w));
+    c.x /= n; c.y /= n; c.z /= n; c.w /= n;
+    double nt[3] = {t[0] * -1.0, t[1] * -1.0, t[2] * -1.0};
+    rot(c, nt, ti);
+    qi[0] = c.x; qi[1] = c.y; qi[2] = c.z; qi[3] = c.w;
+}
+
+int check_params(const dmf_params *p, std::string &why) {
+    if (!p) { why = "params is NULL"; return -1; }
+    if (p->width < 64 || p->height < 64 || p->width > 32768 || p->height > 32768) { why = "width/height out of range [64,32768]"; return -1; }
+    if (p->ncc_half != 3) { why = "only ncc_half == 3 (7x7 window, ref:79) is supported"; return -1; }
+    if (p->border < 4 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 4 and < min(width,height)/2"; return -1; }
+    if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 4096.0)) { why = "step must be > 0 and max_half_len/step <= 4096"; return -1; }
+    if (!(p->fx != 0) || !(p->fy != 0)) { why = "fx, fy must be non-zero"; return -1; }
+    if (!(p->min_cov < p->max_cov)) { why = "min_cov must be < max_cov"; return -1; }
+    return 0;
+}
+
+int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3]) {
+    dmf::KParams K{};
+    const dmf_params &p = c->prm;
+    K.width = p.width; K.height = p.height; K.border = p.border;
+    K.row_begin = c->row_begin; K.row_end = c->row_end;
+    K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
+    K.ncc_thresh = (float)p.ncc_thresh;
+    K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
+    K.step = p.step; K.max_half_len = p.max_half_len; K.min_depth = p.min_depth; K.n_sigma = p.n_sigma;
+    K.min_cov = p.min_cov; K.max_cov = p.max_cov;
+    for (int i = 0; i < 4; ++i) K.q[i] = q[i];
+    for (int i = 0; i < 3; ++i) K.t[i] = t[i];
+    se3_inverse(q, t, K.qi, K.ti);
+    K.curr = d_curr; K.ref = c->d_ref; K.refstat = c->d_refstat;
+    K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.counters = c->d_counters;
+    K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
+    K.flags_pitch = p.width;
+    const int rows = c->row_end - c->row_begin;
+    if (rows > 0) {
+        dim3 grid((p.width - 2 * p.border + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
+        dmf::update_fused_kernel<<<grid, dmf::TILE_PIX, sizeof(dmf::Shared), c->stream>>>(K);
+        CU(cudaGetLastError());
+    }
+    c->frames++;
+    return DMF_OK;
+}
+
+}  // namespace
+
+struct dmf_ctx : dmf_ctx_impl {};
+
+extern "C" {
+
+int dmf_abi_version(void) { return DMF_ABI_VERSION; }
+
+const char *dmf_build_info(void) { return "slamplay_b200 dmf: sm_100a, built " __DATE__ " " __TIME__; }
+
+const char *dmf_last_error(const dmf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int dmf_default_params(dmf_params *p, int width, int height, int inverse_depth) {
+    dmf_ctx_impl *c = nullptr;
+    if (!p || width <= 0 || height <= 0) return fail(c, DMF_ERR_INVALID, "dmf_default_params: bad arguments");
+    std::memset(p, 0, sizeof(*p));
+    p->width = width; p->height = height;
+    p->border = 20;    // ref:72
+    p->ncc_half = 3;   // ref:79
+    if (width == 640 && height == 480) {  // ref:73-78, float literals widened to double
+        p->fx = 481.2f; p->fy = -480.0f; p->cx = 319.5f; p->cy = 239.5f;
+    } else {
+        const double s = (double)width / 640.0;
+        p->fx = (double)481.2f * s; p->fy = -480.0 * s;
+        p->cx = 0.5 * (width - 1); p->cy = 0.5 * (height - 1);
+    }
+    p->step = 0.7; p->max_half_len = 100; p->min_depth = 0.1; p->n_sigma = 3;  // ref:432,422,414,412
+    p->ncc_thresh = 0.85f;                                                     // ref:443
+    if (inverse_depth) { p->min_cov = 0.0001; p->max_cov = 1; }                // ref:82-83
+    else { const double good_error = 0.01; p->min_cov = good_error * good_error; p->max_cov = 10; }  // ref:85-87
+    p->inverse_depth = inverse_depth ? 1 : 0;
+    return DMF_OK;
+}
+
+int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out) {
+    dmf_ctx_impl *c = nullptr;
+    if (!out) return fail(c, DMF_ERR_INVALID, "dmf_create: out is NULL");
+    *out = nullptr;
+    std::string why;
+    if (check_params(params, why)) return fail(c, DMF_ERR_INVALID, "dmf_create: " + why);
+    if (row_begin < 0 || row_end > params->height || row_begin > row_end)
+        return fail(c, DMF_ERR_INVALID, "dmf_create: need 0 <= row_begin <= row_end <= height");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, DMF_ERR_CUDA, std::string("dmf_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(c, DMF_ERR_INVALID, "dmf_create: device index out of range");
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(c, DMF_ERR_CUDA, std::string("dmf_create: device '") + prop.name + "' is not sm_100 (the kernels are built for sm_100a only)");
+    CU(cudaSetDevice(device));
+
+    dmf_ctx *ctx = new (std::nothrow) dmf_ctx();
+    if (!ctx) return fail(c, DMF_ERR_NOMEM, "dmf_create: out of host memory");
+    c = ctx;
+    c->prm = *params;
+    c->device = device;
+    c->band_lo = row_begin; c->band_hi = row_end;
+    c->row_begin = row_begin < params->border ? params->border : row_begin;
+    c->row_end = row_end > params->height - params->border ? params->height - params->border : row_end;
+    if (c->row_end < c->row_begin) c->row_end = c->row_begin;
+    const size_t W = params->width, H = params->height;
+    c->img_pitch = (int)((W + 15) / 16 * 16);
+#define CUX(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e2_ = (call);                                                                         \
+        if (e2_ != cudaSuccess) {                                                                         \
+            int rc_ = fail(nullptr, DMF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2_));   \
+            dmf_destroy(ctx);                                                                             \
+            return rc_;                                                                                   \
+        }                                                                                                 \
+    } while (0)
+    CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUX(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    const size_t img_bytes = (size_t)c->img_pitch * H;
+    CUX(cudaMalloc(&c->d_ref, img_bytes));
+    for (int b = 0; b < 2; ++b) {
+        CUX(cudaMalloc(&c->d_curr[b], img_bytes));
+        CUX(cudaMallocHost(&c->h_stage[b], img_bytes));
+        CUX(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+        CUX(cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming));
+    }
+    CUX(cudaEventCreateWithFlags(&c->ev_ext, cudaEventDisableTiming));
+    CUX(cudaMalloc(&c->d_refstat, W * H * sizeof(int2)));
+    CUX(cudaMalloc(&c->d_depth, W * H * sizeof(double)));
+    CUX(cudaMalloc(&c->d_cov2, W * H * sizeof(double)));
+    CUX(cudaMalloc(&c->d_flags, W * H));
+    CUX(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+    CUX(cudaMalloc(&c->d_eval, sizeof(double)));
+    CUX(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CUX(cudaMemsetAsync(c->d_flags, 0, W * H, c->stream));
+    CUX(cudaMemsetAsync(c->d_refstat, 0, W * H * sizeof(int2), c->stream));
+    CUX(cudaMemsetAsync(c->d_depth, 0, W * H * sizeof(double), c->stream));
+    CUX(cudaMemsetAsync(c->d_cov2, 0, W * H * sizeof(double), c->stream));
+    CUX(cudaFuncSetAttribute(dmf::update_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dmf::Shared)));
+    CUX(cudaStreamSynchronize(c->stream));
+#undef CUX
+    *out = ctx;
+    return DMF_OK;
+}
+
+void dmf_destroy(dmf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_ref);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->d_curr[b]);
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
+    }
+    if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
+    cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int dmf_get_params(const dmf_ctx *ctx, dmf_params *out) {
+    if (!ctx || !out) return fail(nullptr, DMF_ERR_INVALID, "dmf_get_params: NULL argument");
+    *out = ctx->prm;
+    return DMF_OK;
+}
+
+int dmf_get_band(const dmf_ctx *ctx, int *row_begin, int *row_end) {
+    if (!ctx || !row_begin || !row_end) return fail(nullptr, DMF_ERR_INVALID, "dmf_get_band: NULL argument");
+    *row_begin = ctx->row_begin; *row_end = ctx->row_end;
+    return DMF_OK;
+}
+
+static int run_ref_stats(dmf_ctx *c) {
+    const dmf_params &p = c->prm;
+    dim3 blk(32, 8);
+    dim3 grid((p.width - 2 * p.border + 31) / 32, (p.height - 2 * p.border + 7) / 8);
+    dmf::ref_stats_kernel<<<grid, blk, 0, c->stream>>>(c->d_ref, c->img_pitch, p.width, p.height, p.border, c->d_refstat, p.width);
+    CU(cudaGetLastError());
+    c->have_ref = true;
+    return DMF_OK;
+}
+
+int dmf_set_reference(dmf_ctx *c, const uint8_t *ref_host, size_t step) {
+    if (!c || !ref_host) return fail(c, DMF_ERR_INVALID, "dmf_set_reference: NULL argument");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_set_reference: step < width");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy2DAsync(c->d_ref, c->img_pitch, ref_host, step, c->prm.width, c->prm.height, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // the host image may be released on return
+    return run_ref_stats(c);
+}
+
+int dmf_set_reference_device(dmf_ctx *c, const uint8_t *ref_dev, size_t step) {
+    if (!c || !ref_dev) return fail(c, DMF_ERR_INVALID, "dmf_set_reference_device: NULL argument");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_set_reference_device: step < width");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy2DAsync(c->d_ref, c->img_pitch, ref_dev, step, c->prm.width, c->prm.height, cudaMemcpyDeviceToDevice, c->stream));
+    return run_ref_stats(c);
+}
+
+int dmf_fill_state(dmf_ctx *c, double init_depth, double init_cov2) {
+    if (!c) return fail(c, DMF_ERR_INVALID, "dmf_fill_state: NULL context");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->prm.width * c->prm.height;
+    dmf::fill_state_kernel<<<148 * 4, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, n, init_depth, init_cov2);
+    CU(cudaGetLastError());
+    return DMF_OK;
+}
+
+int dmf_upload_state(dmf_ctx *c, const double *depth, size_t depth_step, const double *cov2, size_t cov2_step) {
+    if (!c || !depth || !cov2) return fail(c, DMF_ERR_INVALID, "dmf_upload_state: NULL argument");
+    const size_t rowb = (size_t)c->prm.width * sizeof(double);
+    if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_upload_state: step < width*8");
+    CU(cudaSetDevice(c->device));
+    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
+    if (rows > 0) {
+        CU(cudaMemcpy2DAsync(c->d_depth + (size_t)y0 * c->prm.width, rowb, (const char *)depth + (size_t)y0 * depth_step, depth_step, rowb, rows, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpy2DAsync(c->d_cov2 + (size_t)y0 * c->prm.width, rowb, (const char *)cov2 + (size_t)y0 * cov2_step, cov2_step, rowb, rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+int dmf_download_state(dmf_ctx *c, double *depth, size_t depth_step, double *cov2, size_t cov2_step) {
+    if (!c || !depth || !cov2) return fail(c, DMF_ERR_INVALID, "dmf_download_state: NULL argument");
+    const size_t rowb = (size_t)c->prm.width * sizeof(double);
+    if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_download_state: step < width*8");
+    CU(cudaSetDevice(c->device));
+    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
+    if (rows > 0) {
+        CU(cudaMemcpy2DAsync((char *)depth + (size_t)y0 * depth_step, depth_step, c->d_depth + (size_t)y0 * c->prm.width, rowb, rowb, rows, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpy2DAsync((char *)cov2 + (size_t)y0 * cov2_step, cov2_step, c->d_cov2 + (size_t)y0 * c->prm.width, rowb, rowb, rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+int dmf_update(dmf_ctx *c, const uint8_t *curr_host, size_t step, const double q[4], const double t[3]) {
+    if (!c || !curr_host || !q || !t) return fail(c, DMF_ERR_INVALID, "dmf_update: NULL argument");
+    if (!c->have_ref) return fail(c, DMF_ERR_STATE, "dmf_update: dmf_set_reference() has not been called");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_update: step < width");
+    CU(cudaSetDevice(c->device));
+    const int b = (int)(c->frame_idx & 1);
+    c->frame_idx++;
+    const int W = c->prm.width, H = c->prm.height;
+    // Is the caller's frame pinned (dmf_alloc_pinned / cudaHostRegister)?  Then copy straight from it.
+    cudaPointerAttributes attr{};
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, curr_host) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    const uint8_t *src = curr_host;
+    size_t src_step = step;
+    if (!pinned) {
+        // staging buffer b is free once its previous H2D copy has completed
+        CU(cudaEventSynchronize(c->ev_copied[b]));
+        if (step == (size_t)c->img_pitch) std::memcpy(c->h_stage[b], curr_host, (size_t)step * H);
+        else for (int y = 0; y < H; ++y) std::memcpy(c->h_stage[b] + (size_t)y * c->img_pitch, curr_host + (size_t)y * step, W);
+        src = c->h_stage[b];
+        src_step = c->img_pitch;
+    }
+    // the device buffer b is free once the kernel of two frames ago has consumed it
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, src, src_step, W, H, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    int rc = launch_update(c, c->d_curr[b], c->img_pitch, q, t);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
+    return DMF_OK;
+}
+
+int dmf_update_device(dmf_ctx *c, const uint8_t *curr_dev, size_t step, const double q[4], const double t[3], void *wait_stream) {
+    if (!c || !curr_dev || !q || !t) return fail(c, DMF_ERR_INVALID, "dmf_update_device: NULL argument");
+    if (!c->have_ref) return fail(c, DMF_ERR_STATE, "dmf_update_device: dmf_set_reference() has not been called");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_update_device: step < width");
+    CU(cudaSetDevice(c->device));
+    if (wait_stream) {
+        CU(cudaEventRecord(c->ev_ext, (cudaStream_t)wait_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_ext, 0));
+    }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(curr_dev) & 3u) == 0) && (step % 4 == 0) && step <= 0x7fffffff;
+    if (aligned) return launch_update(c, curr_dev, (int)step, q, t);
+    // unaligned device frame: repack into an internal pitched buffer on the compute stream
+    const int b = (int)(c->frame_idx & 1);
+    c->frame_idx++;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, curr_dev, step, c->prm.width, c->prm.height, cudaMemcpyDeviceToDevice, c->stream));
+    int rc = launch_update(c, c->d_curr[b], c->img_pitch, q, t);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
+    return DMF_OK;
+}
+
+int dmf_sync(dmf_ctx *c) {
+    if (!c) return fail(c, DMF_ERR_INVALID, "dmf_sync: NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+int dmf_read_counters(dmf_ctx *c, dmf_counters *out, int reset) {
+    if (!c || !out) return fail(c, DMF_ERR_INVALID, "dmf_read_counters: NULL argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long h[3];
+    CU(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out->frames = c->frames;
+    out->interior = c->frames * (unsigned long long)(c->row_end - c->row_begin) * (unsigned long long)(c->prm.width - 2 * c->prm.border);
+    out->active = h[0]; out->ncc_evals = h[1]; out->accepted = h[2];
+    if (reset) c->frames = 0;
+    return DMF_OK;
+}
+
+int dmf_enable_flags(dmf_ctx *c, int enable) {
+    if (!c) return fail(c, DMF_ERR_INVALID, "dmf_enable_flags: NULL context");
+    c->flags_on = enable != 0;
+    return DMF_OK;
+}
+
+int dmf_download_flags(dmf_ctx *c, uint8_t *flags_host, size_t step) {
+    if (!c || !flags_host) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: NULL argument");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: step < width");
+    CU(cudaSetDevice(c->device));
+    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
+    if (rows > 0)
+        CU(cudaMemcpy2DAsync(flags_host + (size_t)y0 * step, step, c->d_flags + (size_t)y0 * c->prm.width, c->prm.width, c->prm.width, rows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+int dmf_device_state(dmf_ctx *c, double **depth_dev, double **cov2_dev, size_t *pitch) {
+    if (!c || !depth_dev || !cov2_dev || !pitch) return fail(c, DMF_ERR_INVALID, "dmf_device_state: NULL argument");
+    *depth_dev = c->d_depth; *cov2_dev = c->d_cov2; *pitch = (size_t)c->prm.width * sizeof(double);
+    return DMF_OK;
+}
+
+int dmf_stream(dmf_ctx *c, void **stream) {
+    if (!c || !stream) return fail(c, DMF_ERR_INVALID, "dmf_stream: NULL argument");
+    *stream = (void *)c->stream;
+    return DMF_OK;
+}
+
+int dmf_alloc_pinned(void **ptr, size_t bytes) {
+    dmf_ctx_impl *c = nullptr;
+    if (!ptr) return fail(c, DMF_ERR_INVALID, "dmf_alloc_pinned: NULL argument");
+    CU(cudaMallocHost(ptr, bytes));
+    return DMF_OK;
+}
+
+int dmf_free_pinned(void *ptr) {
+    dmf_ctx_impl *c = nullptr;
+    if (ptr) CU(cudaFreeHost(ptr));
+    return DMF_OK;
+}
+
+int dmf_set_truth(dmf_ctx *c, const double *truth_host, size_t step) {
+    if (!c || !truth_host) return fail(c, DMF_ERR_INVALID, "dmf_set_truth: NULL argument");
+    const size_t rowb = (size_t)c->prm.width * sizeof(double);
+    if (step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_set_truth: step < width*8");
+    CU(cudaSetDevice(c->device));
+    if (!c->d_truth) CU(cudaMalloc(&c->d_truth, rowb * c->prm.height));
+    CU(cudaMemcpy2DAsync(c->d_truth, rowb, truth_host, step, rowb, c->prm.height, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_truth = true;
+    return DMF_OK;
+}
+
+int dmf_evaluate_depth(dmf_ctx *c, double max_variance, double *sum_sq, uint64_t *count) {
+    if (!c || !sum_sq || !count) return fail(c, DMF_ERR_INVALID, "dmf_evaluate_depth: NULL argument");
+    if (!c->have_truth) return fail(c, DMF_ERR_STATE, "dmf_evaluate_depth: dmf_set_truth() has not been called");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_eval, 0, sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
+    if (c->row_end > c->row_begin) {
+        dmf::evaluate_depth_kernel<<<148 * 2, 256, 0, c->stream>>>(c->d_truth, c->d_depth, c->d_cov2, c->prm.width, c->prm.border,
+                                                                   c->prm.width - c->prm.border, c->row_begin, c->row_end, max_variance,
+                                                                   c->d_eval, c->d_counters + 3);
+        CU(cudaGetLastError());
+    }
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(sum_sq, c->d_eval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&n, c->d_counters + 3, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *count = n;
+    return DMF_OK;
+}
+
+int dmf_variance_mask(dmf_ctx *c, double max_variance, uint8_t *mask_host, size_t step) {
+    if (!c || !mask_host) return fail(c, DMF_ERR_INVALID, "dmf_variance_mask: NULL argument");
+    if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_variance_mask: step < width");
+    CU(cudaSetDevice(c->device));
+    const int W = c->prm.width;
+    if (!c->d_mask) CU(cudaMalloc(&c->d_mask, (size_t)W * c->prm.height));
+    const int y0 = c->band_lo, y1 = c->band_hi;
+    if (y1 > y0) {
+        dim3 blk(64, 4), grid((W + 63) / 64, (y1 - y0 + 3) / 4);
+        dmf::variance_mask_kernel<<<grid, blk, 0, c->stream>>>(c->d_cov2, W, W, y0, y1, max_variance, c->d_mask, W);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy2DAsync(mask_host + (size_t)y0 * step, step, c->d_mask + (size_t)y0 * W, W, W, y1 - y0, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+}  // extern "C"

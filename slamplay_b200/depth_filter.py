@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's call surface for the dense monocular depth filter.
+
+Reference: luigifreda/slamplay dense_mapping/test_monocular_mapping.cpp
+
+    void update(const Mat &ref, const Mat &curr, const SE3d &T_C_R, Mat &depth, Mat &depth_cov2);   # :107-112, :355
+
+* `update(ref, curr, T_C_R, depth, depth_cov2)` below has the same name, argument order and
+  in-place semantics (numpy arrays stand in for cv::Mat, `SE3` for Sophus::SE3d).  It is the
+  STRICT drop-in: maps are uploaded, updated on the GPU and downloaded before it returns, as the
+  reference's caller reads them after every call (:292-300).
+* `DepthFilter` is the RESIDENT form north_star describes: depth / depth_cov2 stay in HBM for the
+  whole sequence; only the u8 frame and the 7-double pose cross PCIe per update.
+
+Everything computes through the C ABI of include/dmf.h (libdmf.so, sm_100a).  There is no
+CPU fallback: without the CUDA library or a B200 these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import DmfCounters, DmfParams
+from .se3 import SE3
+
+
+class DmfError(RuntimeError):
+    pass
+
+
+def default_params(width: int = 640, height: int = 480, inverse_depth: bool = False) -> DmfParams:
+    """Reference constants (:72-89) for a width x height image; see dmf_default_params."""
+    p = DmfParams()
+    rc = _lib.load_dmf().dmf_default_params(C.byref(p), int(width), int(height), int(bool(inverse_depth)))
+    if rc != 0:
+        raise DmfError(_lib.load_dmf().dmf_last_error(None).decode())
+    return p
+
+
+def _pose_arrays(T_C_R) -> Tuple[C.Array, C.Array]:
+    if isinstance(T_C_R, SE3):
+        q, t = T_C_R.q, T_C_R.t
+    else:
+        q, t = T_C_R
+    if len(q) != 4 or len(t) != 3:
+        raise ValueError("T_C_R must be an SE3 or a (q_xyzw[4], t[3]) pair")
+    return (C.c_double * 4)(*[float(v) for v in q]), (C.c_double * 3)(*[float(v) for v in t])
+
+
+def _check_u8(name: str, img: np.ndarray, p: DmfParams) -> np.ndarray:
+    if not isinstance(img, np.ndarray) or img.dtype != np.uint8 or img.ndim != 2:
+        raise ValueError(f"{name} must be a 2-D uint8 array (CV_8UC1)")
+    if img.shape != (p.height, p.width):
+        raise ValueError(f"{name} has shape {img.shape}, expected {(p.height, p.width)}")  # MSG_ASSERT at :265
+    if img.strides[1] != 1:
+        raise ValueError(f"{name} must have contiguous rows")
+    return img
+
+
+def _check_f64(name: str, m: np.ndarray, p: DmfParams) -> np.ndarray:
+    if not isinstance(m, np.ndarray) or m.dtype != np.float64 or m.ndim != 2:
+        raise ValueError(f"{name} must be a 2-D float64 array (CV_64F)")
+    if m.shape != (p.height, p.width):
+        raise ValueError(f"{name} has shape {m.shape}, expected {(p.height, p.width)}")
+    if m.strides[1] != 8:
+        raise ValueError(f"{name} must have contiguous rows")
+    return m
+
+
+class DepthFilter:
+    """Resident depth-filter context (one per GPU / row band)."""
+
+    def __init__(self, params: Optional[DmfParams] = None, *, width: int = 640, height: int = 480,
+                 device: int = 0, rows: Optional[Tuple[int, int]] = None, inverse_depth: bool = False):
+        self._lib = _lib.load_dmf()
+        self.params = params.copy() if params is not None else default_params(width, height, inverse_depth)
+        r0, r1 = rows if rows is not None else (0, self.params.height)
+        self._ctx = C.c_void_p()
+        rc = self._lib.dmf_create(C.byref(self.params), int(device), int(r0), int(r1), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.dmf_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise DmfError(f"dmf_create failed ({rc}): {msg}")
+        self.device = int(device)
+        self.rows = (int(r0), int(r1))
+        self._keep = []  # pinned/host frames that must outlive async copies
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.dmf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise DmfError(f"{what} failed ({rc}): {self._lib.dmf_last_error(self._ctx).decode()}")
+
+    # -- inputs ------------------------------------------------------------------------
+    def set_reference(self, ref: np.ndarray) -> None:
+        ref = _check_u8("ref", ref, self.params)
+        self._ck(self._lib.dmf_set_reference(self._ctx, ref.ctypes.data, ref.strides[0]), "dmf_set_reference")
+
+    def set_reference_device(self, ptr: int, step: int) -> None:
+        self._ck(self._lib.dmf_set_reference_device(self._ctx, C.c_void_p(ptr), step), "dmf_set_reference_device")
+
+    def fill_state(self, init_depth: float = 3.0, init_cov2: float = 3.0) -> None:
+        """Mat(h, w, CV_64F, init) of :277-278 (init_depth = init_cov2 = 3.0 at :270,274)."""
+        if not init_cov2 < self.params.max_cov:
+            raise ValueError("Please increase max_cov above the init cov")  # MSG_ASSERT at :276
+        self._ck(self._lib.dmf_fill_state(self._ctx, float(init_depth), float(init_cov2)), "dmf_fill_state")
+
+    def upload_state(self, depth: np.ndarray, depth_cov2: np.ndarray) -> None:
+        d = _check_f64("depth", depth, self.params)
+        c = _check_f64("depth_cov2", depth_cov2, self.params)
+        self._ck(self._lib.dmf_upload_state(self._ctx, d.ctypes.data, d.strides[0], c.ctypes.data, c.strides[0]),
+                 "dmf_upload_state")
+
+    def download_state(self, depth: Optional[np.ndarray] = None, depth_cov2: Optional[np.ndarray] = None):
+        p = self.params
+        if depth is None:
+            depth = np.zeros((p.height, p.width), np.float64)
+        if depth_cov2 is None:
+            depth_cov2 = np.zeros((p.height, p.width), np.float64)
+        d = _check_f64("depth", depth, p)
+        c = _check_f64("depth_cov2", depth_cov2, p)
+        self._ck(self._lib.dmf_download_state(self._ctx, d.ctypes.data, d.strides[0], c.ctypes.data, c.strides[0]),
+                 "dmf_download_state")
+        return depth, depth_cov2
+
+    # -- the hot path --------------------------------------------------------------------
+    def update(self, curr: np.ndarray, T_C_R) -> None:
+        """One reference update() (:355-393) against `curr`; asynchronous."""
+        curr = _check_u8("curr", curr, self.params)
+        q, t = _pose_arrays(T_C_R)
+        self._ck(self._lib.dmf_update(self._ctx, curr.ctypes.data, curr.strides[0], q, t), "dmf_update")
+
+    def update_ptr(self, host_ptr: int, step: int, T_C_R) -> None:
+        q, t = _pose_arrays(T_C_R)
+        self._ck(self._lib.dmf_update(self._ctx, C.c_void_p(host_ptr), step, q, t), "dmf_update")
+
+    def update_device(self, dev_ptr: int, step: int, T_C_R, wait_stream: Optional[int] = None) -> None:
+        q, t = _pose_arrays(T_C_R)
+        self._ck(self._lib.dmf_update_device(self._ctx, C.c_void_p(dev_ptr), step, q, t,
+                                             C.c_void_p(wait_stream) if wait_stream else None), "dmf_update_device")
+
+    def sync(self) -> None:
+        self._ck(self._lib.dmf_sync(self._ctx), "dmf_sync")
+
+    # -- introspection -------------------------------------------------------------------
+    def counters(self, reset: bool = False) -> dict:
+        out = DmfCounters()
+        self._ck(self._lib.dmf_read_counters(self._ctx, C.byref(out), int(reset)), "dmf_read_counters")
+        return out.as_dict()
+
+    def enable_flags(self, on: bool = True) -> None:
+        self._ck(self._lib.dmf_enable_flags(self._ctx, int(on)), "dmf_enable_flags")
+
+    def flags(self) -> np.ndarray:
+        p = self.params
+        f = np.zeros((p.height, p.width), np.uint8)
+        self._ck(self._lib.dmf_download_flags(self._ctx, f.ctypes.data, f.strides[0]), "dmf_download_flags")
+        return f
+
+    def band(self) -> Tuple[int, int]:
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._lib.dmf_get_band(self._ctx, C.byref(a), C.byref(b)), "dmf_get_band")
+        return a.value, b.value
+
+    def device_state(self) -> Tuple[int, int, int]:
+        d, c, pitch = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.dmf_device_state(self._ctx, C.byref(d), C.byref(c), C.byref(pitch)), "dmf_device_state")
+        return d.value, c.value, pitch.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._ck(self._lib.dmf_stream(self._ctx, C.byref(s)), "dmf_stream")
+        return s.value or 0
+
+    # -- "next" rows -------------------------------------------------------
+    def set_truth(self, truth: np.ndarray) -> None:
+        t = _check_f64("truth", truth, self.params)
+        self._ck(self._lib.dmf_set_truth(self._ctx, t.ctypes.data, t.strides[0]), "dmf_set_truth")
+
+    def evaluate_depth(self, max_variance: Optional[float] = None) -> Tuple[float, int]:
+        """evaludateDepth (:569-590): returns (sum of squared errors, count); RMS = sqrt(s/n)."""
+        if max_variance is None:
+            max_variance = 2.0 * self.params.min_cov  # good_cov :89
+        s, n = C.c_double(), C.c_uint64()
+        self._ck(self._lib.dmf_evaluate_depth(self._ctx, float(max_variance), C.byref(s), C.byref(n)), "dmf_evaluate_depth")
+        return s.value, n.value
+
+    def variance_mask(self, max_variance: Optional[float] = None) -> np.ndarray:
+        """getMaskFromVariance (:199-204) for the band rows."""
+        if max_variance is None:
+            max_variance = 2.0 * self.params.min_cov
+        p = self.params
+        m = np.zeros((p.height, p.width), np.uint8)
+        self._ck(self._lib.dmf_variance_mask(self._ctx, float(max_variance), m.ctypes.data, m.strides[0]), "dmf_variance_mask")
+        return m
+
+
+# ---------------------------------------------------------------------------------------------
+# Strict drop-in: the reference's free function.
+_strict_ctx: dict = {}
+
+
+def update(ref: np.ndarray, curr: np.ndarray, T_C_R, depth: np.ndarray, depth_cov2: np.ndarray,
+           params: Optional[DmfParams] = None, device: int = 0) -> None:
+    """void update(const Mat &ref, const Mat &curr, const SE3d &T_C_R, Mat &depth, Mat &depth_cov2)
+
+    Same contract as dense_mapping/test_monocular_mapping.cpp:355-393: `depth` and `depth_cov2`
+    (float64, H x W) are updated in place and are valid on return.  `params` defaults to the
+    reference constants for the image size.  A context per (size, params, device) is cached.
+    """
+    if params is None:
+        if not isinstance(ref, np.ndarray) or ref.ndim != 2:
+            raise ValueError("ref must be a 2-D uint8 array (CV_8UC1)")
+        params = default_params(ref.shape[1], ref.shape[0])
+    key = (bytes(params), int(device))
+    f = _strict_ctx.get(key)
+    if f is None:
+        f = DepthFilter(params, device=device)
+        _strict_ctx[key] = f
+    f.set_reference(ref)
+    f.upload_state(depth, depth_cov2)
+    f.update(curr, T_C_R)
+    f.download_state(depth, depth_cov2)
+
+
+def release_strict_contexts() -> None:
+    for f in _strict_ctx.values():
+        f.close()
+    _strict_ctx.clear()
