@@ -152,6 +152,9 @@ int dmf_read_counters(dmf_ctx *ctx, dmf_counters *out, int reset);
  */
 int dmf_enable_flags(dmf_ctx *ctx, int enable);
 int dmf_download_flags(dmf_ctx *ctx, uint8_t *flags_host, size_t step);
+/* With flags enabled: per-pixel best NCC (ref:430-441) and (trip count of the loop ref:432) << 16 |
+ * index of the winning iteration (0xFFFF: none) of the LAST update; dense W*H arrays. */
+int dmf_download_debug(dmf_ctx *ctx, float *best_ncc_host, int32_t *samples_host);
 
 /*
  * Raw device pointers for the multi-GPU gather (row-band sharding):

@@ -71,6 +71,7 @@ DMF_SYMBOLS = {
     "dmf_read_counters": (C.c_int, [_vp, _P(DmfCounters), C.c_int]),
     "dmf_enable_flags": (C.c_int, [_vp, C.c_int]),
     "dmf_download_flags": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "dmf_download_debug": (C.c_int, [_vp, _vp, _vp]),
     "dmf_device_state": (C.c_int, [_vp, _P(_vp), _P(_vp), _P(C.c_size_t)]),
     "dmf_stream": (C.c_int, [_vp, _P(_vp)]),
     "dmf_alloc_pinned": (C.c_int, [_P(_vp), C.c_size_t]),

@@ -31,6 +31,8 @@ struct dmf_ctx_impl {
     int2 *d_refstat = nullptr;
     double *d_depth = nullptr, *d_cov2 = nullptr, *d_truth = nullptr;
     uint8_t *d_flags = nullptr, *d_mask = nullptr;
+    float *d_dbg_ncc = nullptr;
+    int *d_dbg_n = nullptr;
     unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
     double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
     bool have_ref = false, flags_on = false, have_truth = false;
@@ -96,7 +98,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     for (int i = 0; i < 3; ++i) K.t[i] = t[i];
     se3_inverse(q, t, K.qi, K.ti);
     K.curr = d_curr; K.ref = c->d_ref; K.refstat = c->d_refstat;
-    K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.counters = c->d_counters;
+    K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
     K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
     K.flags_pitch = p.width;
     const int rows = c->row_end - c->row_begin;
@@ -225,6 +227,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     }
     if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
+    cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -387,6 +390,14 @@ int dmf_read_counters(dmf_ctx *c, dmf_counters *out, int reset) {
 
 int dmf_enable_flags(dmf_ctx *c, int enable) {
     if (!c) return fail(c, DMF_ERR_INVALID, "dmf_enable_flags: NULL context");
+    CU(cudaSetDevice(c->device));
+    if (enable && !c->d_dbg_ncc) {
+        const size_t n = (size_t)c->prm.width * c->prm.height;
+        CU(cudaMalloc(&c->d_dbg_ncc, n * sizeof(float)));
+        CU(cudaMalloc(&c->d_dbg_n, n * sizeof(int)));
+        CU(cudaMemsetAsync(c->d_dbg_ncc, 0, n * sizeof(float), c->stream));
+        CU(cudaMemsetAsync(c->d_dbg_n, 0, n * sizeof(int), c->stream));
+    }
     c->flags_on = enable != 0;
     return DMF_OK;
 }
@@ -398,6 +409,17 @@ int dmf_download_flags(dmf_ctx *c, uint8_t *flags_host, size_t step) {
     const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
     if (rows > 0)
         CU(cudaMemcpy2DAsync(flags_host + (size_t)y0 * step, step, c->d_flags + (size_t)y0 * c->prm.width, c->prm.width, c->prm.width, rows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DMF_OK;
+}
+
+int dmf_download_debug(dmf_ctx *c, float *best_ncc_host, int32_t *samples_host) {
+    if (!c || !best_ncc_host || !samples_host) return fail(c, DMF_ERR_INVALID, "dmf_download_debug: NULL argument");
+    if (!c->d_dbg_ncc) return fail(c, DMF_ERR_STATE, "dmf_download_debug: dmf_enable_flags(ctx, 1) has not been called");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->prm.width * c->prm.height;
+    CU(cudaMemcpyAsync(best_ncc_host, c->d_dbg_ncc, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(samples_host, c->d_dbg_n, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return DMF_OK;
 }

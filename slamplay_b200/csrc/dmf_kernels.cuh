@@ -25,7 +25,8 @@
 //  * Current-image taps come from global memory through aligned 32-bit __ldg gathers plus
 //    funnel shifts (texture units filter with 8-bit weights and would break parity).
 //  * arg-max keeps the reference's "first strict maximum" (ref:438) through a 64-bit key
-//    (ordered NCC bits : ~sample index) and shared-memory atomicMax.
+//    (ordered NCC bits : 0xFFFFFFFE - sample index; 0xFFFFFFFF is the "no winner yet" sentinel that
+//    goes with best_ncc = -1.0) and shared-memory atomicMax.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,6 +56,8 @@ struct KParams {
     double *depth;
     double *cov2;
     uint8_t *flags;
+    float *dbg_ncc;  // with write_flags: best NCC per active pixel
+    int *dbg_n;      // with write_flags: (samples << 16) | winning sample index (0xFFFF: none)
     unsigned long long *counters;  // [0]=active [1]=ncc_evals [2]=accepted
     int curr_pitch, ref_pitch, stat_pitch, state_pitch, flags_pitch;  // in elements
 };
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(TILE_PIX, 3) update_fused_kernel(const __grid_
         const float fx = (float)(sx - (double)ix), fy = (float)(sy - (double)iy);
         const float v = ncc_int_moments(P, S.patch[p], ix, iy, fx, fy);
         ++my_evals;
-        const unsigned long long key = ((unsigned long long)ordered_bits(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+        const unsigned long long key = ((unsigned long long)ordered_bits(v) << 32) | (unsigned long long)(0xFFFFFFFEu - (unsigned)k);
         if (v == v && key > S.best[p]) atomicMax(&S.best[p], key);  // first strict maximum ref:438-441
     }
     __syncthreads();
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(TILE_PIX, 3) update_fused_kernel(const __grid_
         if ((unsigned)key == 0xFFFFFFFFu) accepted = false;  // no sample beat -1.0
     }
     if (accepted) {
-        const int k = (int)(0xFFFFFFFFu - (unsigned)S.best[tid]);
+        const int k = (int)(0xFFFFFFFEu - (unsigned)S.best[tid]);
         const double l = sample_l(S.half[tid], P.step, k);
         const double ex = S.dx[tid], ey = S.dy[tid];
         const double cxp = fma(l, ex, S.pmx[tid]), cyp = fma(l, ey, S.pmy[tid]);  // pt_curr
@@ -403,7 +406,13 @@ __global__ void __launch_bounds__(TILE_PIX, 3) update_fused_kernel(const __grid_
         P.depth[(size_t)y * P.state_pitch + x] = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
         P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
     }
-    if (P.write_flags && in_img) P.flags[(size_t)y * P.flags_pitch + x] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
+    if (P.write_flags && in_img) {
+        P.flags[(size_t)y * P.flags_pitch + x] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
+        const unsigned long long key = S.best[tid];
+        P.dbg_ncc[(size_t)y * P.flags_pitch + x] = active ? from_ordered_bits((unsigned)(key >> 32)) : 0.0f;
+        const unsigned kb = ((unsigned)key == 0xFFFFFFFFu) ? 0xFFFFu : (0xFFFFFFFEu - (unsigned)key);
+        P.dbg_n[(size_t)y * P.flags_pitch + x] = active ? ((n << 16) | (int)(kb > 0xFFFEu ? 0xFFFFu : kb)) : 0;
+    }
 
     // counters: warp reduce -> shared -> one global atomic per CTA
     unsigned int a = __popc(__ballot_sync(0xffffffffu, active));

@@ -175,6 +175,15 @@ class DepthFilter:
         self._ck(self._lib.dmf_download_flags(self._ctx, f.ctypes.data, f.strides[0]), "dmf_download_flags")
         return f
 
+    def debug(self):
+        """(best NCC float32 HxW, trip count HxW, winning iteration HxW [-1: none]) of the last update."""
+        p = self.params
+        ncc = np.zeros((p.height, p.width), np.float32)
+        raw = np.zeros((p.height, p.width), np.int32)
+        self._ck(self._lib.dmf_download_debug(self._ctx, ncc.ctypes.data, raw.ctypes.data), "dmf_download_debug")
+        best = raw & 0xFFFF
+        return ncc, raw >> 16, np.where(best == 0xFFFF, -1, best)
+
     def band(self) -> Tuple[int, int]:
         a, b = C.c_int(), C.c_int()
         self._ck(self._lib.dmf_get_band(self._ctx, C.byref(a), C.byref(b)), "dmf_get_band")
