@@ -1,0 +1,193 @@
+"""Row-band sharding of the depth filter across the GPUs of one node.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Pixels are independent
+(dense_mapping/test_monocular_mapping.cpp:366,546-564 touch only their own map entry), so the
+state maps are split into contiguous interior row bands, one per rank; every rank needs the whole
+current frame (an epipolar segment can reach anywhere inside the border).  Per frame, rank 0
+broadcasts the u8 frame; the pose table of the sequence is broadcast once; at the end the bands
+are gathered on rank 0.  There is no exchange inside a frame.
+
+The reference has no distributed code at all; this module is the new piece.
+torch is used for device buffers, streams and the collectives only — the update itself is the
+C-ABI call dmf_update_device() on each rank's context.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .depth_filter import DepthFilter
+from .se3 import SE3
+
+
+def band_rows(height: int, border: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous interior-row band [r0, r1) of `rank`; bands tile [border, height-border) exactly.
+    Rank 0 / world-1 additionally own the top / bottom border rows so that the gathered maps cover
+    the full image."""
+    interior = height - 2 * border
+    base, rem = divmod(interior, world)
+    start = border + rank * base + min(rank, rem)
+    stop = start + base + (1 if rank < rem else 0)
+    if rank == 0:
+        start = 0
+    if rank == world - 1:
+        stop = height
+    return start, stop
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class ShardedDepthFilter:
+    """Depth filter whose state is split into row bands over the ranks of a process group."""
+
+    def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 3):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = params
+        r0, r1 = band_rows(params.height, params.border, self.world, self.rank)
+        self.rows = (r0, r1)
+        self.pitch = (params.width + 15) // 16 * 16
+        self.H, self.W = params.height, params.width
+        self._k = 0
+        self._ring_events = [None] * n_ring
+        self._attach(device, n_ring)
+
+    # The three hooks below are the only places that touch CUDA; tests/test_sharded_gloo.py
+    # overrides them with an oracle-backed band on CPU tensors to exercise the protocol
+    # (band partition, frame / pose broadcast, gather) under gloo with world_size 2.
+    def _attach(self, device, n_ring) -> None:
+        torch = self.torch
+        self.device = torch.cuda.current_device() if device is None else device
+        self.filter = DepthFilter(self.params, device=self.device, rows=self.rows)
+        dev = torch.device("cuda", self.device)
+        self.tdev = dev
+        self.ring = [torch.empty((self.H, self.pitch), dtype=torch.uint8, device=dev) for _ in range(n_ring)]
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.ctx_stream = torch.cuda.ExternalStream(self.filter.stream(), device=dev)
+        d_ptr, c_ptr, pitch = self.filter.device_state()
+        assert pitch == self.W * 8
+        self.depth_t = torch.as_tensor(_DevArray(d_ptr, (self.H, self.W), "<f8"), device=dev)
+        self.cov2_t = torch.as_tensor(_DevArray(c_ptr, (self.H, self.W), "<f8"), device=dev)
+
+    def _set_reference(self, buf) -> None:
+        self.filter.set_reference_device(buf.data_ptr(), self.pitch)
+        self.filter.sync()
+
+    def _launch(self, buf, pose, after_comm: bool) -> None:
+        self.filter.update_device(buf.data_ptr(), self.pitch, pose,
+                                  wait_stream=self.comm_stream.cuda_stream if after_comm else None)
+
+    # -- setup ---------------------------------------------------------------------------
+    def set_reference(self, ref_dev) -> None:
+        """ref_dev: torch uint8 (H, pitch) tensor valid on rank 0; broadcast to all ranks."""
+        torch, dist = self.torch, self.dist
+        buf = ref_dev if self.rank == 0 else torch.empty((self.H, self.pitch), dtype=torch.uint8, device=self.tdev)
+        if self.world > 1:
+            dist.broadcast(buf, src=0, group=self.group)
+            self._sync_current()
+        self._set_reference(buf)
+
+    def _sync_current(self) -> None:
+        if self.tdev.type == "cuda":
+            self.torch.cuda.current_stream().synchronize()
+
+    def fill_state(self, d0: float = 3.0, c0: float = 3.0) -> None:
+        self.filter.fill_state(d0, c0)
+
+    def broadcast_poses(self, poses: Optional[Sequence[SE3]]) -> List[Tuple[tuple, tuple]]:
+        """Rank 0 passes the T_C_R list of the sequence; every rank gets it back (one collective)."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return [(T.q, T.t) for T in poses]
+        n = torch.tensor([len(poses) if self.rank == 0 else 0], dtype=torch.int64, device=self.tdev)
+        dist.broadcast(n, src=0, group=self.group)
+        tab = torch.empty((int(n.item()), 7), dtype=torch.float64, device=self.tdev)
+        if self.rank == 0:
+            tab.copy_(torch.tensor([list(T.q) + list(T.t) for T in poses], dtype=torch.float64))
+        dist.broadcast(tab, src=0, group=self.group)
+        host = tab.cpu().numpy()
+        return [(tuple(r[:4]), tuple(r[4:])) for r in host]
+
+    # -- per frame -------------------------------------------------------------------------
+    def update(self, frame_dev, pose: Tuple[tuple, tuple]) -> None:
+        """frame_dev: torch uint8 (H, pitch) tensor on rank 0 (ignored elsewhere).  Asynchronous:
+        the broadcast runs on a side stream, double-buffered against the previous frame's kernel."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            self._launch(frame_dev, pose, False)
+            return
+        b = self._k % len(self.ring)
+        self._k += 1
+        buf = frame_dev if self.rank == 0 else self.ring[b]
+        if self.tdev.type != "cuda":  # gloo / CPU protocol test: synchronous
+            dist.broadcast(buf, src=0, group=self.group)
+            self._launch(buf, pose, False)
+            return
+        with torch.cuda.stream(self.comm_stream):
+            if self._ring_events[b] is not None:
+                self.comm_stream.wait_event(self._ring_events[b])  # kernel that last read ring[b] is done
+            dist.broadcast(buf, src=0, group=self.group)
+        self._launch(buf, pose, True)
+        ev = torch.cuda.Event()
+        ev.record(self.ctx_stream)
+        self._ring_events[b] = ev
+
+    # -- results ---------------------------------------------------------------------------
+    def gather_state(self):
+        """Gather the bands on rank 0: returns (depth, cov2) torch tensors (H, W) on rank 0, else None."""
+        torch, dist = self.torch, self.dist
+        self._sync_filter()
+        if self.world == 1:
+            return self.depth_t, self.cov2_t
+        r0, r1 = self.rows
+        max_rows = max(band_rows(self.H, self.params.border, self.world, r)[1] - band_rows(self.H, self.params.border, self.world, r)[0]
+                       for r in range(self.world))
+        send = torch.zeros((2, max_rows, self.W), dtype=torch.float64, device=self.depth_t.device)
+        send[0, : r1 - r0] = self.depth_t[r0:r1]
+        send[1, : r1 - r0] = self.cov2_t[r0:r1]
+        if self.rank == 0:
+            recv = [torch.empty_like(send) for _ in range(self.world)]
+            dist.gather(send, recv, dst=0, group=self.group)
+            for r in range(1, self.world):
+                a, b = band_rows(self.H, self.params.border, self.world, r)
+                self.depth_t[a:b] = recv[r][0, : b - a]
+                self.cov2_t[a:b] = recv[r][1, : b - a]
+            self._sync_current()
+            return self.depth_t, self.cov2_t
+        dist.gather(send, None, dst=0, group=self.group)
+        self._sync_current()
+        return None
+
+    def _sync_filter(self) -> None:
+        self.filter.sync()
+
+    def _local_counters(self, reset: bool) -> dict:
+        return self.filter.counters(reset)
+
+    def counters(self, reset: bool = False) -> dict:
+        """Work counters summed over ranks (all ranks get the total)."""
+        torch, dist = self.torch, self.dist
+        c = self._local_counters(reset)
+        if self.world == 1:
+            return c
+        keys = ["interior", "active", "ncc_evals", "accepted"]
+        t = torch.tensor([c[k] for k in keys], dtype=torch.int64, device=self.depth_t.device)
+        dist.all_reduce(t, group=self.group)
+        out = {k: int(v) for k, v in zip(keys, t.tolist())}
+        out["frames"] = c["frames"]
+        return out
+
+    def close(self) -> None:
+        self.filter.close()
