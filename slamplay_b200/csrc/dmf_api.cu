@@ -35,6 +35,12 @@ struct dmf_ctx_impl {
     int *d_dbg_n = nullptr;
     unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
     double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
+    // per-frame scratch of the three-kernel update (setup -> ncc -> fuse)
+    double *d_setup = nullptr;                 // 5 arrays of n_pix doubles
+    unsigned long long *d_best = nullptr;
+    unsigned int *d_units_full = nullptr, *d_units_tail = nullptr;
+    dmf::Ctrl *d_ctrl = nullptr;
+    int n_pix = 0, ncc_grid = 0;
     bool have_ref = false, flags_on = false, have_truth = false;
     unsigned long long frames = 0;
     unsigned long long frame_idx = 0;
@@ -78,7 +84,9 @@ int check_params(const dmf_params *p, std::string &why) {
     if (p->width < 64 || p->height < 64 || p->width > 32768 || p->height > 32768) { why = "width/height out of range [64,32768]"; return -1; }
     if (p->ncc_half != 3) { why = "only ncc_half == 3 (7x7 window, ref:79) is supported"; return -1; }
     if (p->border < 4 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 4 and < min(width,height)/2"; return -1; }
-    if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 4096.0)) { why = "step must be > 0 and max_half_len/step <= 4096"; return -1; }
+    // the work-unit encoding holds chunk indices < 64 (CHUNK = 8 samples): trip count < 512
+    if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 250.0)) { why = "step must be > 0 and max_half_len/step <= 250"; return -1; }
+    if ((long long)(p->width - 2 * p->border) * (p->height - 2 * p->border) >= (1ll << 26)) { why = "more than 2^26 interior pixels"; return -1; }
     if (!(p->fx != 0) || !(p->fy != 0)) { why = "fx, fy must be non-zero"; return -1; }
     if (!(p->min_cov < p->max_cov)) { why = "min_cov must be < max_cov"; return -1; }
     return 0;
@@ -101,10 +109,18 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
     K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
     K.flags_pitch = p.width;
+    K.wi = p.width - 2 * p.border;
+    K.n_pix = c->n_pix;
+    const size_t np = (size_t)c->n_pix;
+    K.s_pmx = c->d_setup; K.s_pmy = c->d_setup + np; K.s_dx = c->d_setup + 2 * np; K.s_dy = c->d_setup + 3 * np;
+    K.s_half = c->d_setup + 4 * np;
+    K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.ctrl = c->d_ctrl;
     const int rows = c->row_end - c->row_begin;
     if (rows > 0) {
-        dim3 grid((p.width - 2 * p.border + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
-        dmf::update_fused_kernel<<<grid, dmf::TILE_PIX, sizeof(dmf::Shared), c->stream>>>(K);
+        dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
+        dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
+        dmf::fuse_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         CU(cudaGetLastError());
     }
     c->frames++;
@@ -206,7 +222,23 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     CUX(cudaMemsetAsync(c->d_refstat, 0, W * H * sizeof(int2), c->stream));
     CUX(cudaMemsetAsync(c->d_depth, 0, W * H * sizeof(double), c->stream));
     CUX(cudaMemsetAsync(c->d_cov2, 0, W * H * sizeof(double), c->stream));
-    CUX(cudaFuncSetAttribute(dmf::update_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dmf::Shared)));
+    {
+        // scratch of the setup -> ncc -> fuse pipeline
+        c->n_pix = (int)((W - 2 * (size_t)params->border) * (size_t)(c->row_end - c->row_begin));
+        const size_t np = c->n_pix > 0 ? (size_t)c->n_pix : 1;
+        const int n_max = (int)(2.0 * params->max_half_len / params->step) + 2;  // trip-count bound of ref:432
+        const size_t max_full = (size_t)(n_max / dmf::CHUNK) + 1;
+        CUX(cudaMalloc(&c->d_setup, 5 * np * sizeof(double)));
+        CUX(cudaMalloc(&c->d_best, np * sizeof(unsigned long long)));
+        CUX(cudaMalloc(&c->d_units_full, np * max_full * sizeof(unsigned int)));
+        CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
+        CUX(cudaMalloc(&c->d_ctrl, sizeof(dmf::Ctrl)));
+        CUX(cudaMemsetAsync(c->d_ctrl, 0, sizeof(dmf::Ctrl), c->stream));
+        int per_sm = 0;
+        CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        c->ncc_grid = prop.multiProcessorCount * per_sm;  // persistent CTAs: one resident wave
+    }
     CUX(cudaStreamSynchronize(c->stream));
 #undef CUX
     *out = ctx;
@@ -228,6 +260,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
+    cudaFree(ctx->d_setup); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -5,28 +5,36 @@
 //   update ref:355-393, epipolarSearch ref:397-447, NCC ref:449-480,
 //   getBilinearInterpolatedValue ref:165-174, updateDepthFilter ref:482-567.
 //
-// Design (DESIGN.md §3 has the full derivation):
-//  * One CTA owns a TILE_W x TILE_H tile of reference pixels and runs three phases in ONE
-//    kernel, so depth / depth_cov2 are read once and written once per frame in HBM:
-//      P1 (thread = pixel, FP64): gate ref:366, projections of mu and mu±3σ ref:402-422,
-//         sample count of the l-loop ref:432; packs the pixel's 7x7 reference patch.
-//      P2 (thread = (pixel, sample), block-local flattened work list built by a prefix sum
-//         over the sample counts): one NCC per item.  Lanes are always full, whatever the
-//         per-pixel search length (0..286 samples).
-//      P3 (thread = pixel, FP64): triangulation + uncertainty + Gaussian fusion ref:482-567.
-//  * NCC arithmetic.  All 49 taps of one NCC share the same four bilinear weights (the tap
-//    offsets are integers, ref:461), so every sum the ZNCC needs is a linear / quadratic form
-//    in (w00,w10,w01,w11) over INTEGER moments of the 8x8 u8 block under the sample:
-//    4 window sums S, 4 cross sums R with the reference patch, 10 Gram sums G.  They are
-//    accumulated exactly with IDP.4A (4 u8 MACs per instruction, 192 per NCC), centred exactly
-//    in int32 (49*R - Sr*S, 49*G - S*S'), and only the final 30-flop combination is FP32.
-//    That is the reference's two-pass (centred) ZNCC up to ~1e-7, with no u8->f32 conversion
-//    in the loop and none of the cancellation of a one-pass FP32 variance.
-//  * Current-image taps come from global memory through aligned 32-bit __ldg gathers plus
-//    funnel shifts (texture units filter with 8-bit weights and would break parity).
-//  * arg-max keeps the reference's "first strict maximum" (ref:438) through a 64-bit key
-//    (ordered NCC bits : 0xFFFFFFFE - sample index; 0xFFFFFFFF is the "no winner yet" sentinel that
-//    goes with best_ncc = -1.0) and shared-memory atomicMax.
+// Per frame three kernels run back to back on the context stream:
+//
+//   setup_kernel  (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
+//                 trip count n of the l-loop ref:432.  The n samples of a pixel are cut into
+//                 work UNITS of at most CHUNK consecutive samples; units are appended to
+//                 per-length lists in HBM (length CHUNK first, ..., length 1 last).
+//   ncc_kernel    (thread = unit)  persistent CTAs pull 32-unit slices of the lists with an
+//                 atomic cursor, so every warp runs units of ONE length (no divergence on the
+//                 search length, which varies 0..286 per pixel) and the chip stays balanced
+//                 whatever the spatial distribution of converged / diverged pixels.  The unit's
+//                 7x7 reference patch lives in registers for all its samples; its best sample
+//                 goes to the pixel's 64-bit arg-max key with one atomicMax.
+//   fuse_kernel   (thread = pixel, FP64)  accept test ref:443, triangulation, uncertainty and
+//                 Gaussian fusion ref:482-567, in place on the HBM-resident maps.
+//
+// NCC arithmetic.  All 49 taps of one NCC share the same four bilinear weights (the tap
+// offsets are integers, ref:461), so every sum the ZNCC needs is a linear / quadratic form
+// in (w00,w10,w01,w11) over INTEGER moments of the 8x8 u8 block under the sample: 4 window
+// sums S, 4 cross sums R with the reference patch, 10 Gram sums G.  They are accumulated
+// exactly with IDP.4A (4 u8 MACs per instruction), centred exactly in int32
+// (49*R - Sr*S, 49*G - S*S'), and only the final ~35-flop combination is FP32.  That is the
+// reference's two-pass (centred) ZNCC up to ~3e-7, with no u8->f32 conversion in the loop and
+// none of the cancellation of a one-pass FP32 variance.
+// Current-image taps come from global memory through aligned 32-bit __ldg gathers plus funnel
+// shifts (texture units filter with 8-bit weights and would break parity).  Adjacent lanes
+// hold adjacent pixels at the same chunk, so their gathers fall into the same cache lines
+// whatever the direction of the epipolar line.
+// The arg-max keeps the reference's "first strict maximum" (ref:438): key = (order-preserving
+// NCC bits : 0xFFFFFFFE - sample index); 0xFFFFFFFF in the low word is the "no winner yet"
+// sentinel that goes with best_ncc = -1.0 (ref:430).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,14 +43,28 @@ namespace dmf {
 
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 8;
-constexpr int TILE_PIX = TILE_W * TILE_H;  // == threads per CTA
+constexpr int TILE_PIX = TILE_W * TILE_H;
+constexpr int CHUNK = 8;          // samples per work unit
+constexpr int CHUNK_BITS = 6;     // unit = (pixel index << CHUNK_BITS) | chunk index   (chunk < 64)
+constexpr int NCC_THREADS = 256;
+constexpr int GRAB = 64;          // units a warp pulls per atomic
 constexpr int NCC_AREA = 49;
 // 1e-10 * (49*255^2)^2 : the reference's epsilon (ref:479) in centred-integer units
 constexpr float NCC_EPS_INT = 1015.2029750625f;
+constexpr unsigned long long KEY_SENTINEL_LO = 0xFFFFFFFFull;
+
+// Per-frame control block in HBM.
+struct Ctrl {
+    unsigned int count[CHUNK + 1];  // count[L] = number of units of length L (L = 1..CHUNK)
+    unsigned int cursor;            // next unclaimed slot of the padded, concatenated lists
+    unsigned int pad[6];
+};
 
 struct KParams {
     int width, height, border;
     int row_begin, row_end;  // interior rows owned by this context
+    int wi;                  // width - 2*border
+    int n_pix;               // interior pixels of the band = wi * (row_end - row_begin)
     int inverse_depth;
     int write_flags;
     float ncc_thresh;
@@ -55,9 +77,15 @@ struct KParams {
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
     double *depth;
     double *cov2;
+    // per-frame scratch, indexed by the band-local interior pixel index
+    double *s_pmx, *s_pmy, *s_dx, *s_dy, *s_half;  // px_mean ref:406, direction ref:419-420, half length ref:421-422
+    unsigned long long *best;                      // arg-max keys
+    unsigned int *units_full;                      // units of length CHUNK
+    unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
+    Ctrl *ctrl;
     uint8_t *flags;
     float *dbg_ncc;  // with write_flags: best NCC per active pixel
-    int *dbg_n;      // with write_flags: (samples << 16) | winning sample index (0xFFFF: none)
+    int *dbg_n;      // with write_flags: (trip count << 16) | winning iteration (0xFFFF: none)
     unsigned long long *counters;  // [0]=active [1]=ncc_evals [2]=accepted
     int curr_pitch, ref_pitch, stat_pitch, state_pitch, flags_pitch;  // in elements
 };
@@ -85,10 +113,19 @@ __device__ __forceinline__ void normalize3(D3 &a) {  // Eigen normalize(): only 
 __device__ __forceinline__ double int2double_fast(int k) {
     return __hiloint2double(0x43300000, (int)((unsigned)k ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
 }
-
 // sample position parameter of iteration k of the loop ref:432, l_k = -half + step*k
 __device__ __forceinline__ double sample_l(double half, double step, int k) {
     return fma(step, int2double_fast(k), -half);
+}
+__device__ __forceinline__ unsigned int ordered_bits(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ unsigned long long key_init() {
+    return ((unsigned long long)ordered_bits(-1.0f) << 32) | KEY_SENTINEL_LO;  // best_ncc = -1.0 ref:430
 }
 
 // ----------------------------------------------------------------------------------------
@@ -115,6 +152,84 @@ __global__ void __launch_bounds__(256) ref_stats_kernel(const uint8_t *__restric
 }
 
 // ----------------------------------------------------------------------------------------
+// K2a: per-pixel setup + work-unit emission.
+__global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__ KParams P) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
+    const int y = P.row_begin + blockIdx.y * TILE_H + (tid / TILE_W);
+    const bool in_img = (x < P.width - P.border) && (y < P.row_end);
+    const int pidx = (y - P.row_begin) * P.wi + (x - P.border);
+
+    int n = 0;
+    bool active = false;
+    if (in_img) {
+        const double c2 = P.cov2[(size_t)y * P.state_pitch + x];
+        active = !(c2 < P.min_cov || c2 > P.max_cov);  // ref:366 — NaN passes the gate
+        P.best[pidx] = key_init();
+        if (active) {
+            const double mu = P.depth[(size_t)y * P.state_pitch + x];
+            const double sigma = sqrt(c2);  // ref:377
+            D3 f_ref{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};  // ref:207-212
+            normalize3(f_ref);
+            const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
+            double d_min, d_max;
+            if (P.inverse_depth) {  // ref:407-410
+                const double inv_mu = 1.0 / mu;
+                d_min = 1.0 / (inv_mu + P.n_sigma * sigma);
+                d_max = 1.0 / (inv_mu - P.n_sigma * sigma);
+            } else {  // ref:412
+                d_min = mu - P.n_sigma * sigma;
+                d_max = mu + P.n_sigma * sigma;
+            }
+            if (d_min < P.min_depth) d_min = P.min_depth;  // ref:414
+            // cam2px ref:215-219 of the three points
+            const double zm = fma(Rf.z, mu, P.t[2]), z0 = fma(Rf.z, d_min, P.t[2]), z1 = fma(Rf.z, d_max, P.t[2]);
+            const double pmx = fma(Rf.x, mu, P.t[0]) * P.fx / zm + P.cx, pmy = fma(Rf.y, mu, P.t[1]) * P.fy / zm + P.cy;
+            const double p0x = fma(Rf.x, d_min, P.t[0]) * P.fx / z0 + P.cx, p0y = fma(Rf.y, d_min, P.t[1]) * P.fy / z0 + P.cy;
+            const double p1x = fma(Rf.x, d_max, P.t[0]) * P.fx / z1 + P.cx, p1y = fma(Rf.y, d_max, P.t[1]) * P.fy / z1 + P.cy;
+            double lx = p1x - p0x, ly = p1y - p0y;  // ref:418
+            const double len2 = lx * lx + ly * ly;
+            const double len = sqrt(len2);
+            double half = 0.5 * len;  // ref:421
+            if (len2 > 0) { lx /= len; ly /= len; }            // ref:420 (guarded normalize)
+            if (half > P.max_half_len) half = P.max_half_len;  // ref:422
+            // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
+            if (half >= 0) {
+                n = (int)(2.0 * half / P.step) + 1;
+                while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
+                while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
+            }
+            P.s_pmx[pidx] = pmx; P.s_pmy[pidx] = pmy; P.s_dx[pidx] = lx; P.s_dy[pidx] = ly; P.s_half[pidx] = half;
+        }
+        if (P.write_flags) P.dbg_n[(size_t)y * P.flags_pitch + x] = n;
+    }
+
+    // ---- emit work units (warp-cooperative, chunk-major so that adjacent slots hold adjacent pixels)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_full = n / CHUNK, tail = n % CHUNK;
+    const int m_full = __reduce_max_sync(0xffffffffu, n_full);
+    if (m_full > 0) {
+        const int tot = __reduce_add_sync(0xffffffffu, n_full);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&P.ctrl->count[CHUNK], (unsigned)tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int j = 0; j < m_full; ++j) {
+            const unsigned bal = __ballot_sync(0xffffffffu, n_full > j);
+            if (n_full > j) P.units_full[base + __popc(bal & lt_mask)] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)j;
+            base += __popc(bal);
+        }
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, tail);
+    const int leader = __ffs(grp) - 1;
+    unsigned tbase = 0;
+    if (lane == leader && tail > 0) tbase = atomicAdd(&P.ctrl->count[tail], (unsigned)__popc(grp));
+    tbase = __shfl_sync(0xffffffffu, tbase, leader);
+    if (tail > 0)
+        P.units_tail[(size_t)(tail - 1) * P.n_pix + tbase + __popc(grp & lt_mask)] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)n_full;
+}
+
+// ----------------------------------------------------------------------------------------
 // Loads 8 bytes starting at an arbitrary byte address from 4-byte aligned words.
 __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint32_t &lo, uint32_t &hi) {
     uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
@@ -124,74 +239,46 @@ __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint3
 
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
-// Per-pixel shared-memory record written by P1 and read by P2/P3.
-struct __align__(16) RefPatch {
-    uint32_t row[14];  // rows dy=-3..3: (lo = bytes dx -3..0, hi = bytes dx 1..3 and a zero byte)
-    int sum;           // Sr
-    int den1;          // 49*sum r^2 - Sr^2
-};
-
-struct Shared {
-    RefPatch patch[TILE_PIX];
-    double pmx[TILE_PIX], pmy[TILE_PIX];  // px_mean_curr ref:406
-    double dx[TILE_PIX], dy[TILE_PIX];    // epipolar_direction ref:419-420
-    double half[TILE_PIX];                // half_length ref:421-422
-    unsigned long long best[TILE_PIX];    // arg-max key
-    int offs[TILE_PIX + 1];               // exclusive prefix sum of the sample counts
-    int warp_sum[TILE_PIX / 32];
-    unsigned int cnt_active, cnt_eval, cnt_accept;
-};
-
-__device__ __forceinline__ unsigned int ordered_bits(float f) {
-    unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_ordered_bits(unsigned int u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
-// One NCC (ref:449-480) of reference pixel record `rp` against the current image at the
-// sub-pixel position whose integer part is (ix,iy) and bilinear fractions (fx,fy).
-__device__ __forceinline__ float ncc_int_moments(const KParams &P, const RefPatch &rp, int ix, int iy, float fx,
-                                                 float fy) {
+// One NCC (ref:449-480) of the reference patch (Rlo/Rhi rows, Sr, den1) against the current image
+// at the sub-pixel position whose integer part is (ix,iy) and bilinear fractions (fx,fy).
+__device__ __forceinline__ float ncc_int_moments(const KParams &P, const uint32_t (&Rlo)[7], const uint32_t (&Rhi)[7],
+                                                 int Sr, float den1f, int ix, int iy, float fx, float fy) {
     const uint8_t *base = P.curr + (size_t)(iy - 3) * P.curr_pitch + (ix - 3);
-    unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - mis);
     const unsigned sh = mis * 8u;
     const int pitch_w = P.curr_pitch >> 2;
     const uint32_t ONES = 0x01010101u;
-
-    // reference rows (16-byte shared loads)
-    const uint4 *rq = reinterpret_cast<const uint4 *>(rp.row);
-    uint4 r0 = rq[0], r1 = rq[1], r2 = rq[2], r3 = rq[3];
-    const uint32_t Rlo[7] = {r0.x, r0.z, r1.x, r1.z, r2.x, r2.z, r3.x};
-    const uint32_t Rhi[7] = {r0.y, r0.w, r1.y, r1.w, r2.y, r2.w, r3.y};
-    const int Sr = (int)r3.z, den1 = (int)r3.w;
 
     // all 24 gathers first (memory-level parallelism), then the integer moments
     uint32_t lo[8], hi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) load_row8(wp + j * pitch_w, sh, lo[j], hi[j]);
 
-    // accumulators: top = block row 0, mid = rows 1..6, bot = row 7
+    // accumulators: t = block row 0, m = rows 1..6, b = row 7
     int s0t = 0, s0m = 0, s0b = 0, s1t = 0, s1m = 0, s1b = 0;  // row sums, column window a=0 / a=1
-    int q0t = 0, q0m = 0, q0b = 0, q1t = 0, q1m = 0, q1b = 0;  // sum of squares
+    int q0t = 0, q0m = 0, q0b = 0, q1t = 0, q1m = 0, q1b = 0;  // sums of squares
     int ht = 0, hm = 0, hb = 0;                                // horizontal neighbour products
     int v0 = 0, v1 = 0, d01 = 0, d10 = 0;                      // vertical / diagonal products (rows j, j+1)
     int R00 = 0, R10 = 0, R01 = 0, R11 = 0;                    // cross sums with the reference patch
     uint32_t p0l = 0, p0h = 0, p1l = 0, p1h = 0;               // previous row
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint32_t x0l = lo[j], x0h = hi[j] & 0x00FFFFFFu;                       // columns 0..6
-        const uint32_t x1l = __funnelshift_r(lo[j], hi[j], 8), x1h = hi[j] >> 8;     // columns 1..7
-        int s0 = dp4(x0l, ONES, dp4(x0h, ONES, 0));
-        int s1 = dp4(x1l, ONES, dp4(x1h, ONES, 0));
-        int q0 = dp4(x0l, x0l, dp4(x0h, x0h, 0));
-        int q1 = dp4(x1l, x1l, dp4(x1h, x1h, 0));
-        int h = dp4(x0l, x1l, dp4(x0h, x1h, 0));
-        if (j == 0) { s0t = s0; s1t = s1; q0t = q0; q1t = q1; ht = h; }
-        else if (j == 7) { s0b = s0; s1b = s1; q0b = q0; q1b = q1; hb = h; }
-        else { s0m += s0; s1m += s1; q0m += q0; q1m += q1; hm += h; }
+        const uint32_t x0l = lo[j], x0h = hi[j] & 0x00FFFFFFu;                    // columns 0..6
+        const uint32_t x1l = __funnelshift_r(lo[j], hi[j], 8), x1h = hi[j] >> 8;  // columns 1..7
+        if (j == 0) {
+            s0t = dp4(x0l, ONES, dp4(x0h, ONES, 0)); s1t = dp4(x1l, ONES, dp4(x1h, ONES, 0));
+            q0t = dp4(x0l, x0l, dp4(x0h, x0h, 0));   q1t = dp4(x1l, x1l, dp4(x1h, x1h, 0));
+            ht = dp4(x0l, x1l, dp4(x0h, x1h, 0));
+        } else if (j == 7) {
+            s0b = dp4(x0l, ONES, dp4(x0h, ONES, 0)); s1b = dp4(x1l, ONES, dp4(x1h, ONES, 0));
+            q0b = dp4(x0l, x0l, dp4(x0h, x0h, 0));   q1b = dp4(x1l, x1l, dp4(x1h, x1h, 0));
+            hb = dp4(x0l, x1l, dp4(x0h, x1h, 0));
+        } else {
+            s0m = dp4(x0l, ONES, dp4(x0h, ONES, s0m)); s1m = dp4(x1l, ONES, dp4(x1h, ONES, s1m));
+            q0m = dp4(x0l, x0l, dp4(x0h, x0h, q0m));   q1m = dp4(x1l, x1l, dp4(x1h, x1h, q1m));
+            hm = dp4(x0l, x1l, dp4(x0h, x1h, hm));
+        }
         if (j > 0) {
             v0 = dp4(p0l, x0l, dp4(p0h, x0h, v0));
             v1 = dp4(p1l, x1l, dp4(p1h, x1h, v1));
@@ -225,155 +312,146 @@ __device__ __forceinline__ float ncc_int_moments(const KParams &P, const RefPatc
     num = fmaf(w01, (float)cR01, num);
     num = fmaf(w11, (float)cR11, num);
     // den2 = w^T G w
+    const float g0010 = (float)G0010, g0001 = (float)G0001, g0011 = (float)G0011;
+    const float g1001 = (float)G1001, g1011 = (float)G1011, g0111 = (float)G0111;
     float a0 = w00 * (float)G0000;
-    a0 = fmaf(w10, (float)G0010, a0); a0 = fmaf(w01, (float)G0001, a0); a0 = fmaf(w11, (float)G0011, a0);
-    float a1 = w00 * (float)G0010;
-    a1 = fmaf(w10, (float)G1010, a1); a1 = fmaf(w01, (float)G1001, a1); a1 = fmaf(w11, (float)G1011, a1);
-    float a2 = w00 * (float)G0001;
-    a2 = fmaf(w10, (float)G1001, a2); a2 = fmaf(w01, (float)G0101, a2); a2 = fmaf(w11, (float)G0111, a2);
-    float a3 = w00 * (float)G0011;
-    a3 = fmaf(w10, (float)G1011, a3); a3 = fmaf(w01, (float)G0111, a3); a3 = fmaf(w11, (float)G1111, a3);
+    a0 = fmaf(w10, g0010, a0); a0 = fmaf(w01, g0001, a0); a0 = fmaf(w11, g0011, a0);
+    float a1 = w00 * g0010;
+    a1 = fmaf(w10, (float)G1010, a1); a1 = fmaf(w01, g1001, a1); a1 = fmaf(w11, g1011, a1);
+    float a2 = w00 * g0001;
+    a2 = fmaf(w10, g1001, a2); a2 = fmaf(w01, (float)G0101, a2); a2 = fmaf(w11, g0111, a2);
+    float a3 = w00 * g0011;
+    a3 = fmaf(w10, g1011, a3); a3 = fmaf(w01, g0111, a3); a3 = fmaf(w11, (float)G1111, a3);
     float den2 = w00 * a0;
     den2 = fmaf(w10, a1, den2); den2 = fmaf(w01, a2, den2); den2 = fmaf(w11, a3, den2);
     den2 = fmaxf(den2, 0.0f);
-    const float dd = fmaf((float)den1, den2, NCC_EPS_INT);
+    const float dd = fmaf(den1f, den2, NCC_EPS_INT);
     float r = rsqrtf(dd);
     r = r * fmaf(-0.5f * dd * r, r, 1.5f);  // one Newton step: MUFU.RSQ is only ~2 ulp
     return num * r;
 }
 
+// K2b: NCC over the work units.
+__global__ void __launch_bounds__(NCC_THREADS, 2) ncc_kernel(const __grid_constant__ KParams P) {
+    const int lane = threadIdx.x & 31;
+    // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
+    unsigned counts[CHUNK + 1];
+    unsigned total = 0;
+#pragma unroll
+    for (int c = CHUNK; c >= 1; --c) {
+        counts[c] = P.ctrl->count[c];
+        total += (counts[c] + 31u) & ~31u;
+    }
+    unsigned my_evals = 0;
+
+    for (;;) {
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(&P.ctrl->cursor, (unsigned)GRAB);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= total) break;
+#pragma unroll 1
+        for (int sub = 0; sub < GRAB / 32; ++sub) {
+            const unsigned w0 = g + sub * 32;  // warp-uniform slot base (32-aligned)
+            if (w0 >= total) break;
+            // segment of this warp (uniform): unit length L, first slot, number of units
+            int L = 0;
+            unsigned start = 0, cnt = 0, acc = 0;
+#pragma unroll
+            for (int c = CHUNK; c >= 1; --c) {
+                const unsigned padded = (counts[c] + 31u) & ~31u;
+                if (w0 >= acc && w0 < acc + padded) { L = c; start = acc; cnt = counts[c]; }
+                acc += padded;
+            }
+            const unsigned idx = w0 - start + lane;
+            if (idx >= cnt) continue;
+            const unsigned unit = (L == CHUNK) ? P.units_full[idx] : P.units_tail[(size_t)(L - 1) * P.n_pix + idx];
+            const int pidx = (int)(unit >> CHUNK_BITS);
+            const int k0 = (int)(unit & ((1u << CHUNK_BITS) - 1u)) * CHUNK;
+            const int yl = pidx / P.wi;
+            const int x = P.border + (pidx - yl * P.wi), y = P.row_begin + yl;
+
+            // reference patch of (x,y) into registers
+            uint32_t Rlo[7], Rhi[7];
+            {
+                const uint8_t *rb = P.ref + (size_t)(y - 3) * P.ref_pitch + (x - 3);
+                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rb) & 3u);
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(rb - mis);
+                const int pw = P.ref_pitch >> 2;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    load_row8(wp + j * pw, mis * 8u, Rlo[j], Rhi[j]);
+                    Rhi[j] &= 0x00FFFFFFu;
+                }
+            }
+            const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
+            const float den1f = (float)st.y;
+            const double half = P.s_half[pidx], pmx = P.s_pmx[pidx], pmy = P.s_pmy[pidx];
+            const double ex = P.s_dx[pidx], ey = P.s_dy[pidx];
+
+            float best_v = -1.0f;  // ref:430
+            int best_k = -1;
+#pragma unroll 1
+            for (int j = 0; j < L; ++j) {
+                const int k = k0 + j;
+                const double l = sample_l(half, P.step, k);
+                const double sx = fma(l, ex, pmx);  // ref:433
+                const double sy = fma(l, ey, pmy);
+                // inside() ref:222-224
+                const bool ok = sx >= P.border && sy >= P.border && sx + P.border < P.width && sy + P.border <= P.height;
+                if (!ok) continue;
+                const int ix = (int)sx, iy = (int)sy;  // positive: trunc == floor
+                const float fx = (float)(sx - (double)ix), fy = (float)(sy - (double)iy);
+                const float v = ncc_int_moments(P, Rlo, Rhi, st.x, den1f, ix, iy, fx, fy);
+                ++my_evals;
+                if (v > best_v) { best_v = v; best_k = k; }  // first strict maximum ref:438-441
+            }
+            if (best_k >= 0) {
+                const unsigned long long key = ((unsigned long long)ordered_bits(best_v) << 32) |
+                                               (unsigned long long)(0xFFFFFFFEu - (unsigned)best_k);
+                atomicMax(&P.best[pidx], key);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
+    if (lane == 0 && my_evals) atomicAdd(&P.counters[1], (unsigned long long)my_evals);
+}
+
 // ----------------------------------------------------------------------------------------
-// K2: the fused per-frame update.
-__global__ void __launch_bounds__(TILE_PIX, 3) update_fused_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Shared &S = *reinterpret_cast<Shared *>(smem_raw);
+// K2c: accept test + depth-filter fusion, in place.  Also re-arms the control block.
+__global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ KParams P) {
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
     const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
     const int y = P.row_begin + blockIdx.y * TILE_H + (tid / TILE_W);
     const bool in_img = (x < P.width - P.border) && (y < P.row_end);
+    const int pidx = (y - P.row_begin) * P.wi + (x - P.border);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) {
+        reinterpret_cast<unsigned *>(P.ctrl)[tid] = 0;  // ncc_kernel of this frame is done (stream order)
+    }
 
-    if (tid == 0) { S.cnt_active = 0; S.cnt_eval = 0; S.cnt_accept = 0; }
-
-    // ------------------------------------------------------------------ P1
-    double mu = 0, c2 = 0;
-    D3 f_ref{0, 0, 1};
-    int n = 0;
-    bool active = false;
+    bool active = false, accepted = false;
+    double c2 = 0;
+    unsigned long long key = 0;
     if (in_img) {
         c2 = P.cov2[(size_t)y * P.state_pitch + x];
-        active = !(c2 < P.min_cov || c2 > P.max_cov);  // ref:366 — NaN passes the gate
+        active = !(c2 < P.min_cov || c2 > P.max_cov);  // same gate as setup_kernel: the maps are untouched in between
     }
     if (active) {
-        mu = P.depth[(size_t)y * P.state_pitch + x];
-        const double sigma = sqrt(c2);  // ref:377
-        f_ref = D3{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};  // ref:207-212
-        normalize3(f_ref);
-        const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
-        double d_min, d_max;
-        if (P.inverse_depth) {  // ref:407-410
-            const double inv_mu = 1.0 / mu;
-            d_min = 1.0 / (inv_mu + P.n_sigma * sigma);
-            d_max = 1.0 / (inv_mu - P.n_sigma * sigma);
-        } else {  // ref:412
-            d_min = mu - P.n_sigma * sigma;
-            d_max = mu + P.n_sigma * sigma;
-        }
-        if (d_min < P.min_depth) d_min = P.min_depth;  // ref:414
-        // cam2px ref:215-219 of the three points
-        const double zm = fma(Rf.z, mu, P.t[2]), z0 = fma(Rf.z, d_min, P.t[2]), z1 = fma(Rf.z, d_max, P.t[2]);
-        const double pmx = fma(Rf.x, mu, P.t[0]) * P.fx / zm + P.cx, pmy = fma(Rf.y, mu, P.t[1]) * P.fy / zm + P.cy;
-        const double p0x = fma(Rf.x, d_min, P.t[0]) * P.fx / z0 + P.cx, p0y = fma(Rf.y, d_min, P.t[1]) * P.fy / z0 + P.cy;
-        const double p1x = fma(Rf.x, d_max, P.t[0]) * P.fx / z1 + P.cx, p1y = fma(Rf.y, d_max, P.t[1]) * P.fy / z1 + P.cy;
-        double lx = p1x - p0x, ly = p1y - p0y;  // ref:418
-        const double len2 = lx * lx + ly * ly;
-        const double len = sqrt(len2);
-        double half = 0.5 * len;  // ref:421
-        if (len2 > 0) { lx /= len; ly /= len; }  // ref:420 (guarded normalize)
-        if (half > P.max_half_len) half = P.max_half_len;  // ref:422
-        // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
-        if (half >= 0) {
-            n = (int)(2.0 * half / P.step) + 1;
-            while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
-            while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
-        }
-        S.pmx[tid] = pmx; S.pmy[tid] = pmy; S.dx[tid] = lx; S.dy[tid] = ly; S.half[tid] = half;
-        // pack the 7x7 reference patch of (x,y)
-        const uint8_t *rb = P.ref + (size_t)(y - 3) * P.ref_pitch + (x - 3);
-        unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rb) & 3u);
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(rb - mis);
-        const int pw = P.ref_pitch >> 2;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            uint32_t lo, hi;
-            load_row8(wp + j * pw, mis * 8u, lo, hi);
-            S.patch[tid].row[2 * j] = lo;
-            S.patch[tid].row[2 * j + 1] = hi & 0x00FFFFFFu;
-        }
-        const int2 st = P.refstat[(size_t)y * P.stat_pitch + x];
-        S.patch[tid].sum = st.x;
-        S.patch[tid].den1 = st.y;
-    }
-    S.best[tid] = ((unsigned long long)ordered_bits(-1.0f) << 32) | 0xFFFFFFFFull;  // best_ncc = -1.0 ref:430
-
-    // block-wide exclusive prefix sum of n
-    int incl = n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) S.warp_sum[warp] = incl;
-    __syncthreads();
-    int wbase = 0;
-#pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; ++w) wbase += (w < warp) ? S.warp_sum[w] : 0;
-    S.offs[tid] = wbase + incl - n;
-    if (tid == TILE_PIX - 1) S.offs[TILE_PIX] = wbase + incl;
-    __syncthreads();
-    const int total = S.offs[TILE_PIX];
-
-    // ------------------------------------------------------------------ P2
-    unsigned int my_evals = 0;
-    for (int item = tid; item < total; item += TILE_PIX) {
-        // pixel of this item: largest p with offs[p] <= item
-        int lo = 0, hi = TILE_PIX - 1;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int mid = (lo + hi + 1) >> 1;
-            if (S.offs[mid] <= item) lo = mid; else hi = mid - 1;
-        }
-        const int p = lo;
-        const int k = item - S.offs[p];
-        const double l = sample_l(S.half[p], P.step, k);
-        const double sx = fma(l, S.dx[p], S.pmx[p]);  // ref:433
-        const double sy = fma(l, S.dy[p], S.pmy[p]);
-        // inside() ref:222-224
-        const bool ok = sx >= P.border && sy >= P.border && sx + P.border < P.width && sy + P.border <= P.height;
-        if (!ok) continue;
-        const int ix = (int)sx, iy = (int)sy;  // positive: trunc == floor
-        const float fx = (float)(sx - (double)ix), fy = (float)(sy - (double)iy);
-        const float v = ncc_int_moments(P, S.patch[p], ix, iy, fx, fy);
-        ++my_evals;
-        const unsigned long long key = ((unsigned long long)ordered_bits(v) << 32) | (unsigned long long)(0xFFFFFFFEu - (unsigned)k);
-        if (v == v && key > S.best[p]) atomicMax(&S.best[p], key);  // first strict maximum ref:438-441
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ P3
-    bool accepted = false;
-    if (active) {
-        const unsigned long long key = S.best[tid];
+        key = P.best[pidx];
         const float best = from_ordered_bits((unsigned)(key >> 32));
-        accepted = !(best < P.ncc_thresh);  // ref:443
-        if ((unsigned)key == 0xFFFFFFFFu) accepted = false;  // no sample beat -1.0
+        accepted = !(best < P.ncc_thresh) && ((unsigned)key != 0xFFFFFFFFu);  // ref:443; sentinel: nothing beat -1.0
     }
     if (accepted) {
-        const int k = (int)(0xFFFFFFFEu - (unsigned)S.best[tid]);
-        const double l = sample_l(S.half[tid], P.step, k);
-        const double ex = S.dx[tid], ey = S.dy[tid];
-        const double cxp = fma(l, ex, S.pmx[tid]), cyp = fma(l, ey, S.pmy[tid]);  // pt_curr
+        const double mu = P.depth[(size_t)y * P.state_pitch + x];
+        const int k = (int)(0xFFFFFFFEu - (unsigned)key);
+        const double half = P.s_half[pidx];
+        const double ex = P.s_dx[pidx], ey = P.s_dy[pidx];
+        const double l = sample_l(half, P.step, k);
+        const double cxp = fma(l, ex, P.s_pmx[pidx]), cyp = fma(l, ey, P.s_pmy[pidx]);  // pt_curr
         // updateDepthFilter ref:482-567
+        D3 f_ref{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};
+        normalize3(f_ref);
         D3 f_curr{(cxp - P.cx) / P.fx, (cyp - P.cy) / P.fy, 1.0};
         normalize3(f_curr);
         const D3 t{P.ti[0], P.ti[1], P.ti[2]};
@@ -407,29 +485,19 @@ __global__ void __launch_bounds__(TILE_PIX, 3) update_fused_kernel(const __grid_
         P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
     }
     if (P.write_flags && in_img) {
-        P.flags[(size_t)y * P.flags_pitch + x] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
-        const unsigned long long key = S.best[tid];
-        P.dbg_ncc[(size_t)y * P.flags_pitch + x] = active ? from_ordered_bits((unsigned)(key >> 32)) : 0.0f;
+        const size_t o = (size_t)y * P.flags_pitch + x;
+        P.flags[o] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
+        P.dbg_ncc[o] = active ? from_ordered_bits((unsigned)(key >> 32)) : 0.0f;
         const unsigned kb = ((unsigned)key == 0xFFFFFFFFu) ? 0xFFFFu : (0xFFFFFFFEu - (unsigned)key);
-        P.dbg_n[(size_t)y * P.flags_pitch + x] = active ? ((n << 16) | (int)(kb > 0xFFFEu ? 0xFFFFu : kb)) : 0;
+        const int trips = P.dbg_n[o] & 0xFFFF;
+        P.dbg_n[o] = active ? ((trips << 16) | (int)(kb > 0xFFFEu ? 0xFFFFu : kb)) : 0;
     }
-
-    // counters: warp reduce -> shared -> one global atomic per CTA
-    unsigned int a = __popc(__ballot_sync(0xffffffffu, active));
-    unsigned int c = __popc(__ballot_sync(0xffffffffu, accepted));
-    unsigned int e = my_evals;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    // counters: one global atomic per warp
+    const unsigned a = __popc(__ballot_sync(0xffffffffu, active));
+    const unsigned c = __popc(__ballot_sync(0xffffffffu, accepted));
     if (lane == 0) {
-        atomicAdd(&S.cnt_active, a);
-        atomicAdd(&S.cnt_accept, c);
-        atomicAdd(&S.cnt_eval, e);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (S.cnt_active) atomicAdd(&P.counters[0], (unsigned long long)S.cnt_active);
-        if (S.cnt_eval) atomicAdd(&P.counters[1], (unsigned long long)S.cnt_eval);
-        if (S.cnt_accept) atomicAdd(&P.counters[2], (unsigned long long)S.cnt_accept);
+        if (a) atomicAdd(&P.counters[0], (unsigned long long)a);
+        if (c) atomicAdd(&P.counters[2], (unsigned long long)c);
     }
 }
 
@@ -458,7 +526,6 @@ __global__ void __launch_bounds__(256) evaluate_depth_kernel(const double *__res
         s += e * e;
         n++;
     }
-    // block reduction
     __shared__ double ss[8];
     __shared__ unsigned long long sn[8];
 #pragma unroll
