@@ -62,7 +62,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     build = PKG / "build"
     build.mkdir(exist_ok=True)
     ccbin = ["-ccbin", _host_cxx()]
-    out1 = _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")], build / "dmf_api.ptxas.log")
+    extra = os.environ.get("DMF_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DDMF_NCC_MIN_BLOCKS=3
+    out1 = _run([nvcc, *NVCC_FLAGS, *extra, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")], build / "dmf_api.ptxas.log")
     # the renderer must not contract a*b+c into FMA (bit-identical with the g++ build)
     out2 = _run([nvcc, *NVCC_FLAGS, *ccbin, "-fmad=false", "-c", str(CSRC / "synth.cu"), "-o", str(build / "synth.o")], build / "synth.ptxas.log")
     _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "synth.o"), "-lcudart"])

@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — the first gate.
+
+Tolerances (BASELINE.json north_star): depth within 1e-3 relative on >= 95 % of interior pixels;
+accept/reject (NCC >= 0.85f, ref:443) and covariance-gate (ref:366) decisions differing on <= 0.5 % of
+pixels.  Measured margins are far tighter (1e-6 / 0 mismatches); tighter secondary asserts keep it so."""
+import ctypes as C
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from parity import (MAX_DECISION_MISMATCH, MIN_DEPTH_AGREE, class_mismatch, depth_agreement, flag_mismatch)
+from slamplay_b200.se3 import SE3
+from slamplay_b200.synth import make_sequence
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def DF():
+    from slamplay_b200.depth_filter import DepthFilter
+    return DepthFilter
+
+
+def run_pair(DF, seq, frames, n_updates, rows=None, stride=1, init=(3.0, 3.0), state=None, check_flags=True):
+    """GPU and oracle side by side; returns final maps of both and the worst per-frame decision mismatch."""
+    p = seq.params
+    h, w = seq.shape
+    f = DF(p)
+    f.set_reference(frames[0])
+    if state is None:
+        f.fill_state(*init)
+        d_ref, c_ref = np.full((h, w), init[0]), np.full((h, w), init[1])
+    else:
+        d_ref, c_ref = state[0].copy(), state[1].copy()
+        f.upload_state(d_ref, c_ref)
+    f.enable_flags(check_flags)
+    r0, r1 = rows if rows else (p.border, h - p.border)
+    ys = range(r0, r1, stride)
+    worst = 0.0
+    oc = oracle.Counters()
+    for i in range(1, n_updates + 1):
+        T = seq.T_C_R(i)
+        f.update(frames[i], T)
+        fl_ref = np.zeros((h, w), np.uint8)
+        oracle.update(p, frames[0], frames[i], T.q, T.t, d_ref, c_ref, rows=(r0, r1), row_stride=stride, flags=fl_ref, counters=oc)
+        if check_flags:
+            worst = max(worst, flag_mismatch(p, f.flags(), fl_ref, ys))
+    d, c = f.download_state()
+    cnt = f.counters()
+    f.close()
+    return d, c, d_ref, c_ref, worst, ys, cnt, oc.as_dict()
+
+
+def test_remode640_sequence(DF, seq640):
+    """BASELINE.json config 2 (shortened): 640x480 REMODE-shaped, every interior pixel, 5 updates."""
+    seq, frames = seq640
+    d, c, d_ref, c_ref, worst, ys, cnt, oc = run_pair(DF, seq, frames, 5)
+    p = seq.params
+    agree = depth_agreement(p, d, d_ref)
+    assert agree >= MIN_DEPTH_AGREE, agree
+    assert worst <= MAX_DECISION_MISMATCH and class_mismatch(p, c, c_ref) <= MAX_DECISION_MISMATCH
+    # observed margins: keep them
+    assert depth_agreement(p, d, d_ref, rtol=1e-6) > 0.9999
+    assert worst < 1e-4
+    for k in ("interior", "active", "ncc_evals", "accepted"):
+        assert abs(cnt[k] - oc[k]) <= 1e-4 * max(oc[k], 1), (k, cnt[k], oc[k])
+    # border pixels are never touched (ref:357,363)
+    assert (d[:p.border] == 3.0).all() and (d[:, :p.border] == 3.0).all() and (c[-p.border:] == 3.0).all()
+
+
+def test_golden_sequence_from_compiled_reference(DF):
+    """GPU vs the fixture produced by the compiled reference TU (tests/golden/make_golden.py)."""
+    g = np.load(G / "remode640_ref_update.npz")
+    n = int(g["n_frames"])
+    seq = make_sequence("remode_640x480", n_frames=n)
+    frames = [seq.render_host(i) for i in range(n)]
+    assert [hashlib.sha256(f.tobytes()).hexdigest() for f in frames] == list(g["frame_sha"])
+    f = DF(seq.params)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    for i in range(1, n):
+        f.update(frames[i], (g["poses"][i - 1][:4], g["poses"][i - 1][4:]))
+    d, c = f.download_state()
+    f.close()
+    step = int(g["row_step"])
+    rows = range(0, 480, step)
+    p = seq.params
+    assert depth_agreement(p, d, _expand(g["depth_rows"], step, d.shape), rows) >= MIN_DEPTH_AGREE
+    assert depth_agreement(p, d, _expand(g["depth_rows"], step, d.shape), rows, rtol=1e-6) > 0.9999
+    assert class_mismatch(p, c, _expand(g["cov2_rows"], step, c.shape), rows) <= MAX_DECISION_MISMATCH
+
+
+def _expand(rows_arr, step, shape):
+    full = np.zeros(shape)
+    full[::step] = rows_arr
+    return full
+
+
+def test_ncc_values_against_oracle(DF, seq640):
+    """Best NCC per pixel (ref:430-441) from the integer-moment kernel vs the FP64 two-pass oracle."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    f.enable_flags(True)
+    T = seq.T_C_R(2)
+    f.update(frames[2], T)
+    ncc, trips, k = f.debug()
+    d, c = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    oncc = np.zeros((h, w), np.float32)
+    on = np.zeros((h, w), np.int32)
+    oracle.update(p, frames[0], frames[2], T.q, T.t, d, c, dbg_ncc=oncc, dbg_n=on)
+    I = (slice(20, h - 20), slice(20, w - 20))
+    assert np.abs(ncc[I] - oncc[I]).max() < 2e-6
+    assert (trips[I] >= on[I]).all()  # trip count >= NCC calls (samples outside the border are skipped)
+    f.close()
+
+
+def test_kitti_shaped_forward_motion(DF):
+    """BASELINE.json config 3 (shortened): 1241x376 (odd width -> padded pitch), radial epipolar lines."""
+    seq = make_sequence("kitti_1241x376", n_frames=5)
+    frames = [seq.render_host(i) for i in range(seq.n_frames)]
+    d, c, d_ref, c_ref, worst, ys, cnt, oc = run_pair(DF, seq, frames, 4, stride=6)
+    p = seq.params
+    assert depth_agreement(p, d, d_ref, ys) >= MIN_DEPTH_AGREE
+    assert depth_agreement(p, d, d_ref, ys, rtol=1e-6) > 0.999
+    assert worst <= MAX_DECISION_MISMATCH and class_mismatch(p, c, c_ref, ys) <= MAX_DECISION_MISMATCH
+
+
+def test_inverse_depth_variant(DF):
+    """USE_INVERSE_DEPTH_FOR_FILTERING (ref:63): thresholds ref:82-83, init cov 0.5 ref:272."""
+    seq = make_sequence("remode_640x480", n_frames=4, inverse_depth=True)
+    frames = [seq.render_host(i) for i in range(seq.n_frames)]
+    d, c, d_ref, c_ref, worst, ys, _, _ = run_pair(DF, seq, frames, 3, stride=4, init=(3.0, 0.5))
+    p = seq.params
+    assert depth_agreement(p, d, d_ref, ys) >= MIN_DEPTH_AGREE
+    assert worst <= MAX_DECISION_MISMATCH and class_mismatch(p, c, c_ref, ys) <= MAX_DECISION_MISMATCH
+
+
+def test_edge_states_nan_converged_diverged(DF, seq640):
+    """ref:366: NaN passes the gate and stays NaN; converged / diverged pixels are bit-identical afterwards."""
+    seq, frames = seq640
+    h, w = seq.shape
+    rng = np.random.default_rng(11)
+    depth = rng.uniform(1.5, 3.5, (h, w))
+    cov2 = 10.0 ** rng.uniform(-5, 1.2, (h, w))
+    depth[::37, ::41] = np.nan
+    cov2[::53, ::29] = np.nan
+    d, c, d_ref, c_ref, worst, ys, _, _ = run_pair(DF, seq, frames, 2, state=(depth, cov2))
+    p = seq.params
+    assert worst <= MAX_DECISION_MISMATCH
+    assert depth_agreement(p, d, d_ref) >= MIN_DEPTH_AGREE
+    skip = (cov2 < p.min_cov) | (cov2 > p.max_cov)
+    assert np.array_equal(d[skip], depth[skip], equal_nan=True) and np.array_equal(c[skip], cov2[skip], equal_nan=True)
+    assert np.isnan(c[::53, ::29]).all()
+    nan_d = np.isnan(depth) & ~skip
+    assert np.isnan(d[nan_d][:]).all()  # NaN depth -> zero samples -> stays NaN
+
+
+def test_zero_baseline_nan_poison(DF, seq640):
+    """|t| = 0: acos(0/0) (ref:527) poisons every accepted pixel with NaN, in the reference and here."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(2.0, 0.5)
+    f.enable_flags(True)
+    f.update(frames[0], SE3.identity())
+    fl = f.flags()
+    d, c = f.download_state()
+    f.close()
+    d_ref, c_ref = np.full((h, w), 2.0), np.full((h, w), 0.5)
+    fl_ref = np.zeros((h, w), np.uint8)
+    oracle.update(p, frames[0], frames[0], (0, 0, 0, 1), (0, 0, 0), d_ref, c_ref, flags=fl_ref)
+    assert flag_mismatch(p, fl, fl_ref) <= MAX_DECISION_MISMATCH
+    I = (slice(20, h - 20), slice(20, w - 20))
+    assert (np.isnan(d[I]) == np.isnan(d_ref[I])).mean() > 0.995
+    assert np.isnan(d[I]).mean() > 0.9
+
+
+def test_strict_dropin_update_function(DF, seq640):
+    """The reference's free function: update(ref, curr, T_C_R, depth, depth_cov2) in place (ref:355)."""
+    from slamplay_b200.depth_filter import release_strict_contexts, update
+    seq, frames = seq640
+    h, w = seq.shape
+    depth, cov2 = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    d_ref, c_ref = depth.copy(), cov2.copy()
+    for i in (1, 2):
+        T = seq.T_C_R(i)
+        update(frames[0], frames[i], T, depth, cov2)
+        oracle.update(seq.params, frames[0], frames[i], T.q, T.t, d_ref, c_ref)
+    release_strict_contexts()
+    assert depth_agreement(seq.params, depth, d_ref, rtol=1e-6) > 0.9999
+    with pytest.raises(ValueError):
+        update(frames[0][:100], frames[1], seq.T_C_R(1), depth, cov2)  # MSG_ASSERT-like size check (ref:265)
+
+
+def test_strided_host_buffers_and_unaligned_device_frames(DF, seq640):
+    """cv::Mat::step larger than the row (ROI views) and a device frame whose pointer is not 4-byte aligned."""
+    import torch
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    big = np.zeros((h, w + 37), np.uint8)
+    big[:, 5:5 + w] = frames[2]
+    view = big[:, 5:5 + w]
+    dbig = np.full((h, w + 3), 3.0)
+    cbig = np.full((h, w + 3), 3.0)
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.upload_state(dbig[:, 1:1 + w], cbig[:, 1:1 + w])
+    T = seq.T_C_R(2)
+    f.update(view, T)
+    d1, c1 = f.download_state()
+    # same update from an odd device address
+    f.fill_state(3.0, 3.0)
+    dev = torch.zeros(h * w + 16, dtype=torch.uint8, device="cuda")
+    dev[1:1 + h * w] = torch.from_numpy(frames[2].reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    f.update_device(dev.data_ptr() + 1, w, T)
+    d2, c2 = f.download_state()
+    f.close()
+    assert np.array_equal(d1, d2, equal_nan=True) and np.array_equal(c1, c2, equal_nan=True)
+    d_ref, c_ref = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    oracle.update(p, frames[0], frames[2], T.q, T.t, d_ref, c_ref, rows=(20, 460), row_stride=8)
+    assert depth_agreement(p, d1, d_ref, range(20, 460, 8), rtol=1e-6) > 0.9999
+
+
+def test_band_contexts_are_bit_identical_to_one_context(DF, seq640):
+    """Row-band sharding invariant: results do not depend on the partition."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    whole = DF(p)
+    bands = [DF(p, rows=(0, 200)), DF(p, rows=(200, 333)), DF(p, rows=(333, h))]
+    for f in [whole] + bands:
+        f.set_reference(frames[0])
+        f.fill_state(3.0, 3.0)
+    for i in (1, 2, 3):
+        for f in [whole] + bands:
+            f.update(frames[i], seq.T_C_R(i))
+    d, c = whole.download_state()
+    d2, c2 = np.zeros((h, w)), np.zeros((h, w))
+    tot = {"active": 0, "ncc_evals": 0, "accepted": 0, "interior": 0}
+    for f in bands:
+        f.download_state(d2, c2)
+        for k in tot:
+            tot[k] += f.counters()[k]
+    cw = whole.counters()
+    for f in [whole] + bands:
+        f.close()
+    assert np.array_equal(d, d2, equal_nan=True) and np.array_equal(c, c2, equal_nan=True)
+    assert all(tot[k] == cw[k] for k in tot)
+
+
+def test_full_size_properties_hd(DF):
+    """BASELINE.json config 4 size (1920x1080): determinism (two runs bit-identical), exact parity on a row
+    subset against the oracle, work counters consistent."""
+    import torch
+    seq = make_sequence("hd_1920x1080", n_frames=5)
+    p = seq.params
+    h, w = seq.shape
+    pitch = (w + 15) // 16 * 16
+    dev = torch.zeros((seq.n_frames, h, pitch), dtype=torch.uint8, device="cuda")
+    for i in range(seq.n_frames):
+        seq.render_device(i, dev[i].data_ptr(), pitch, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(2):
+        f = DF(p)
+        f.set_reference_device(dev[0].data_ptr(), pitch)
+        f.fill_state(3.0, 3.0)
+        for i in range(1, seq.n_frames):
+            f.update_device(dev[i].data_ptr(), pitch, seq.T_C_R(i))
+        outs.append(f.download_state() + (f.counters(),))
+        f.close()
+    assert np.array_equal(outs[0][0], outs[1][0], equal_nan=True) and np.array_equal(outs[0][1], outs[1][1], equal_nan=True)
+    cnt = outs[0][2]
+    assert cnt["interior"] == 4 * (h - 40) * (w - 40) and cnt["accepted"] <= cnt["active"] <= cnt["interior"]
+    host = dev[:, :, :w].cpu().numpy()
+    rows = (20, h - 20)
+    d_ref, c_ref = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    for i in range(1, seq.n_frames):
+        T = seq.T_C_R(i)
+        oracle.update(p, host[0], host[i], T.q, T.t, d_ref, c_ref, rows=rows, row_stride=64)
+    ys = range(20, h - 20, 64)
+    assert depth_agreement(p, outs[0][0], d_ref, ys) >= MIN_DEPTH_AGREE
+    assert depth_agreement(p, outs[0][0], d_ref, ys, rtol=1e-6) > 0.99
+    assert class_mismatch(p, outs[0][1], c_ref, ys) <= MAX_DECISION_MISMATCH
+
+
+def test_gpu_renderer_is_bit_identical_to_cpu_renderer():
+    import torch
+    seq = make_sequence("tiny", width=320, height=240, n_frames=3)
+    h, w = seq.shape
+    img = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    dist = torch.zeros((h, w), dtype=torch.float64, device="cuda")
+    seq.render_device(2, img.data_ptr(), w, dist.data_ptr(), w * 8, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cpu_img, cpu_dist = seq.render_host(2, with_distance=True)
+    assert np.array_equal(img.cpu().numpy(), cpu_img)
+    assert np.array_equal(dist.cpu().numpy(), cpu_dist)
+
+
+def test_evaluate_depth_and_variance_mask(DF, seq640):
+    """'next' rows SURVEY.md §8f: evaludateDepth ref:569-590 and getMaskFromVariance ref:199-204 on the device."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    _, gt = seq.render_host(0, with_distance=True)
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    for i in range(1, 6):
+        f.update(frames[i], seq.T_C_R(i))
+    f.set_truth(gt)
+    d, c = f.download_state()
+    thr = float(np.median(c[20:-20, 20:-20]))
+    s, n = f.evaluate_depth(thr)
+    mask = f.variance_mask(thr)
+    f.close()
+    so, no = C.c_double(), C.c_uint64()
+    po = oracle.to_params(p)
+    oracle.lib().dmo_evaluate_depth(C.byref(po), gt.ctypes.data, gt.strides[0], d.ctypes.data, d.strides[0], c.ctypes.data,
+                                    c.strides[0], thr, 0, h, C.byref(so), C.byref(no))
+    assert n == no.value and np.isclose(s, so.value, rtol=1e-10)
+    m_ref = np.zeros((h, w), np.uint8)
+    oracle.lib().dmo_variance_mask(w, h, c.ctypes.data, c.strides[0], thr, m_ref.ctypes.data, w)
+    assert np.array_equal(mask, m_ref)
+
+
+def test_api_errors(DF, seq640):
+    from slamplay_b200.depth_filter import DmfError
+    seq, frames = seq640
+    f = DF(seq.params)
+    with pytest.raises(DmfError, match="set_reference"):
+        f.update(frames[1], seq.T_C_R(1))
+    with pytest.raises(ValueError):
+        f.set_reference(frames[0].astype(np.float32))
+    with pytest.raises(ValueError, match="max_cov"):
+        f.fill_state(3.0, 11.0)  # MSG_ASSERT(init_cov2 < max_cov) ref:276
+    f.close()
+
+
+def test_sharded_filter_world1(DF, seq640):
+    """ShardedDepthFilter with a single rank is the plain resident filter."""
+    import torch
+    from slamplay_b200.sharded import ShardedDepthFilter
+    seq, frames = seq640
+    h, w = seq.shape
+    pitch = (w + 15) // 16 * 16
+    dev = torch.zeros((4, h, pitch), dtype=torch.uint8, device="cuda")
+    for i in range(4):
+        dev[i, :, :w] = torch.from_numpy(frames[i]).cuda()
+    torch.cuda.synchronize()
+    sf = ShardedDepthFilter(seq.params, device=0)
+    sf.set_reference(dev[0])
+    sf.fill_state(3.0, 3.0)
+    poses = sf.broadcast_poses([seq.T_C_R(i) for i in range(4)])
+    for i in range(1, 4):
+        sf.update(dev[i], poses[i])
+    d, c = sf.gather_state()
+    d = d.cpu().numpy()
+    sf.close()
+    d_ref, c_ref = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    for i in range(1, 4):
+        T = seq.T_C_R(i)
+        oracle.update(seq.params, frames[0], frames[i], T.q, T.t, d_ref, c_ref, rows=(20, 460), row_stride=8)
+    assert depth_agreement(seq.params, d, d_ref, range(20, 460, 8), rtol=1e-6) > 0.9999
