@@ -36,10 +36,12 @@ struct dmf_ctx_impl {
     unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
     double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
     // per-frame scratch of the three-kernel update (setup -> ncc -> fuse)
-    double *d_setup = nullptr;                 // 5 arrays of n_pix doubles
+    dmf::PixelRec *d_rec = nullptr;            // n_pix 64-byte records
     unsigned long long *d_best = nullptr;
     unsigned int *d_units_full = nullptr, *d_units_tail = nullptr;
     dmf::Ctrl *d_ctrl = nullptr;
+    int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
+    int2 *d_mom2 = nullptr;
     int n_pix = 0, ncc_grid = 0;
     bool have_ref = false, flags_on = false, have_truth = false;
     unsigned long long frames = 0;
@@ -98,7 +100,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.width = p.width; K.height = p.height; K.border = p.border;
     K.row_begin = c->row_begin; K.row_end = c->row_end;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
-    K.ncc_thresh = (float)p.ncc_thresh;
+    K.ncc_thresh = p.ncc_thresh;
     K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
     K.step = p.step; K.max_half_len = p.max_half_len; K.min_depth = p.min_depth; K.n_sigma = p.n_sigma;
     K.min_cov = p.min_cov; K.max_cov = p.max_cov;
@@ -111,13 +113,14 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.flags_pitch = p.width;
     K.wi = p.width - 2 * p.border;
     K.n_pix = c->n_pix;
-    const size_t np = (size_t)c->n_pix;
-    K.s_pmx = c->d_setup; K.s_pmy = c->d_setup + np; K.s_dx = c->d_setup + 2 * np; K.s_dy = c->d_setup + 3 * np;
-    K.s_half = c->d_setup + 4 * np;
+    K.rec = c->d_rec;
+    K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width;
     K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.ctrl = c->d_ctrl;
     const int rows = c->row_end - c->row_begin;
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
+        dim3 mgrid((p.width - 7 + 31) / 32, (p.height - 7 + 7) / 8);
+        dmf::moments_kernel<<<mgrid, 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width);
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         dmf::fuse_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
@@ -228,11 +231,13 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
         const size_t np = c->n_pix > 0 ? (size_t)c->n_pix : 1;
         const int n_max = (int)(2.0 * params->max_half_len / params->step) + 2;  // trip-count bound of ref:432
         const size_t max_full = (size_t)(n_max / dmf::CHUNK) + 1;
-        CUX(cudaMalloc(&c->d_setup, 5 * np * sizeof(double)));
+        CUX(cudaMalloc(&c->d_rec, np * sizeof(dmf::PixelRec)));
         CUX(cudaMalloc(&c->d_best, np * sizeof(unsigned long long)));
         CUX(cudaMalloc(&c->d_units_full, np * max_full * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_ctrl, sizeof(dmf::Ctrl)));
+        CUX(cudaMalloc(&c->d_mom1, W * H * sizeof(int4)));
+        CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(int2)));
         CUX(cudaMemsetAsync(c->d_ctrl, 0, sizeof(dmf::Ctrl), c->stream));
         int per_sm = 0;
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
@@ -260,7 +265,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_setup); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -23,18 +23,23 @@
 // NCC arithmetic.  All 49 taps of one NCC share the same four bilinear weights (the tap
 // offsets are integers, ref:461), so every sum the ZNCC needs is a linear / quadratic form
 // in (w00,w10,w01,w11) over INTEGER moments of the 8x8 u8 block under the sample: 4 window
-// sums S, 4 cross sums R with the reference patch, 10 Gram sums G.  They are accumulated
-// exactly with IDP.4A (4 u8 MACs per instruction), centred exactly in int32
-// (49*R - Sr*S, 49*G - S*S'), and only the final ~35-flop combination is FP32.  That is the
-// reference's two-pass (centred) ZNCC up to ~3e-7, with no u8->f32 conversion in the loop and
-// none of the cancellation of a one-pass FP32 variance.
-// Current-image taps come from global memory through aligned 32-bit __ldg gathers plus funnel
-// shifts (texture units filter with 8-bit weights and would break parity).  Adjacent lanes
-// hold adjacent pixels at the same chunk, so their gathers fall into the same cache lines
-// whatever the direction of the epipolar line.
-// The arg-max keeps the reference's "first strict maximum" (ref:438): key = (order-preserving
-// NCC bits : 0xFFFFFFFE - sample index); 0xFFFFFFFF in the low word is the "no winner yet"
-// sentinel that goes with best_ncc = -1.0 (ref:430).
+// sums S, 4 cross sums R with the reference patch, 10 Gram sums G, all exact in int32, centred
+// exactly in int32 (49*R - Sr*S, 49*G - S*S').
+//   * S and the 10 centred Gram sums depend only on the current frame and the integer position
+//     of the block: moments_kernel computes them ONCE per frame for every block position
+//     (IDP.4A, 4 u8 MACs per instruction) into a 24 B/px table in HBM; a sample reads 5 vector
+//     loads from it instead of redoing ~136 dp4a.
+//   * the 4 cross sums need the reference patch: 56 IDP.4A per sample from aligned 32-bit
+//     __ldg gathers of the block plus funnel shifts (texture units filter with 8-bit weights and
+//     would break parity).
+//   * the final combination (bilinear weights, w^T G w, 1/sqrt) runs in FP64 on the otherwise
+//     idle FP64 pipe, so the NCC agrees with the reference's two-pass FP64 ZNCC to ~1e-13 and
+//     the arg-max / 0.85 decisions are the reference's except for exact ties.
+// Adjacent lanes hold adjacent pixels at the same chunk, so their gathers fall into the same
+// cache lines whatever the direction of the epipolar line.
+// The arg-max keeps the reference's "first strict maximum" (ref:438): 64-bit key =
+// (52-bit mantissa of ncc + 3.0, i.e. fixed point with 2^-51 resolution) << 9 | (510 - sample
+// index); low bits 511 mark the "no winner yet" sentinel that goes with best_ncc = -1.0 (ref:430).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,12 +51,19 @@ constexpr int TILE_H = 8;
 constexpr int TILE_PIX = TILE_W * TILE_H;
 constexpr int CHUNK = 8;          // samples per work unit
 constexpr int CHUNK_BITS = 6;     // unit = (pixel index << CHUNK_BITS) | chunk index   (chunk < 64)
-constexpr int NCC_THREADS = 256;
+#ifndef DMF_NCC_THREADS
+#define DMF_NCC_THREADS 256
+#endif
+#ifndef DMF_NCC_MIN_BLOCKS
+#define DMF_NCC_MIN_BLOCKS 2
+#endif
+constexpr int NCC_THREADS = DMF_NCC_THREADS;
 constexpr int GRAB = 64;          // units a warp pulls per atomic
 constexpr int NCC_AREA = 49;
 // 1e-10 * (49*255^2)^2 : the reference's epsilon (ref:479) in centred-integer units
-constexpr float NCC_EPS_INT = 1015.2029750625f;
-constexpr unsigned long long KEY_SENTINEL_LO = 0xFFFFFFFFull;
+constexpr double NCC_EPS_INT = 1015.2029750625;
+constexpr unsigned KEY_IDX_BITS = 9;          // sample index < 510
+constexpr unsigned KEY_SENTINEL_LO = 511u;
 
 // Per-frame control block in HBM.
 struct Ctrl {
@@ -60,6 +72,18 @@ struct Ctrl {
     unsigned int pad[6];
 };
 
+// Per-pixel record of one frame (64 B = half a cache line, four 16-byte vectors): everything
+// ncc_kernel / fuse_kernel need about an active pixel, so a work unit starts with ONE line fetch.
+struct __align__(16) PixelRec {
+    double2 pm;        // px_mean_curr ref:406
+    double2 dir;       // epipolar_direction ref:419-420
+    double half;       // half_length ref:421-422
+    int nSr;           // -(sum of the 49 reference bytes)
+    int den1;          // 49*sum r^2 - (sum r)^2
+    int4 xy;           // pixel coordinates (x, y, -, -)
+};
+static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
+
 struct KParams {
     int width, height, border;
     int row_begin, row_end;  // interior rows owned by this context
@@ -67,7 +91,7 @@ struct KParams {
     int n_pix;               // interior pixels of the band = wi * (row_end - row_begin)
     int inverse_depth;
     int write_flags;
-    float ncc_thresh;
+    double ncc_thresh;
     double fx, fy, cx, cy;
     double step, max_half_len, min_depth, n_sigma, min_cov, max_cov;
     double q[4], t[3];    // T_C_R (unit quaternion x,y,z,w + translation)
@@ -75,19 +99,21 @@ struct KParams {
     const uint8_t *curr;  // pitched, 4-byte aligned rows
     const uint8_t *ref;
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
+    const int4 *mom1;     // per block position of the current frame: {S, cQ, cH, cV}   (moments_kernel)
+    const int2 *mom2;     //                                          {cD1, cD2}
     double *depth;
     double *cov2;
     // per-frame scratch, indexed by the band-local interior pixel index
-    double *s_pmx, *s_pmy, *s_dx, *s_dy, *s_half;  // px_mean ref:406, direction ref:419-420, half length ref:421-422
+    PixelRec *rec;                                 // written by setup_kernel for active pixels
     unsigned long long *best;                      // arg-max keys
     unsigned int *units_full;                      // units of length CHUNK
     unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
     Ctrl *ctrl;
     uint8_t *flags;
-    float *dbg_ncc;  // with write_flags: best NCC per active pixel
+    float *dbg_ncc;  // with write_flags: best NCC per active pixel (rounded to f32)
     int *dbg_n;      // with write_flags: (trip count << 16) | winning iteration (0xFFFF: none)
     unsigned long long *counters;  // [0]=active [1]=ncc_evals [2]=accepted
-    int curr_pitch, ref_pitch, stat_pitch, state_pitch, flags_pitch;  // in elements
+    int curr_pitch, ref_pitch, stat_pitch, state_pitch, flags_pitch, mom_pitch;  // in elements
 };
 
 // ----------------------------------------------------------------------------------------
@@ -117,16 +143,20 @@ __device__ __forceinline__ double int2double_fast(int k) {
 __device__ __forceinline__ double sample_l(double half, double step, int k) {
     return fma(step, int2double_fast(k), -half);
 }
-__device__ __forceinline__ unsigned int ordered_bits(float f) {
-    unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+// arg-max key: ncc in [-1,1] -> ncc + 3.0 in [2,4): the 52 mantissa bits are an order-preserving
+// fixed-point code with 2^-51 resolution.
+__device__ __forceinline__ unsigned long long ncc_key(double ncc, int k) {
+    double c = fmin(fmax(ncc, -1.0), 1.0) + 3.0;
+    if (c >= 4.0) c = 3.9999999999999996;
+    const unsigned long long m = (unsigned long long)__double_as_longlong(c) & 0x000FFFFFFFFFFFFFull;
+    return (m << KEY_IDX_BITS) | (unsigned long long)(510u - (unsigned)k);
 }
-__device__ __forceinline__ float from_ordered_bits(unsigned int u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+__device__ __forceinline__ double key_ncc(unsigned long long key) {
+    return __longlong_as_double((long long)((key >> KEY_IDX_BITS) | 0x4000000000000000ull)) - 3.0;
 }
-__device__ __forceinline__ unsigned long long key_init() {
-    return ((unsigned long long)ordered_bits(-1.0f) << 32) | KEY_SENTINEL_LO;  // best_ncc = -1.0 ref:430
-}
+__device__ __forceinline__ bool key_has_winner(unsigned long long key) { return ((unsigned)key & 511u) != KEY_SENTINEL_LO; }
+__device__ __forceinline__ int key_index(unsigned long long key) { return 510 - (int)((unsigned)key & 511u); }
+__device__ __forceinline__ unsigned long long key_init() { return (unsigned long long)KEY_SENTINEL_LO; }  // best_ncc = -1.0 ref:430
 
 // ----------------------------------------------------------------------------------------
 // K1: once per reference frame — reference-patch statistics (ref half of NCC, ref:458-459,468,476)
@@ -200,7 +230,12 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
                 while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
                 while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
             }
-            P.s_pmx[pidx] = pmx; P.s_pmy[pidx] = pmy; P.s_dx[pidx] = lx; P.s_dy[pidx] = ly; P.s_half[pidx] = half;
+            const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
+            PixelRec *rec = P.rec + pidx;  // four 16-byte vector stores
+            rec->pm = make_double2(pmx, pmy);
+            rec->dir = make_double2(lx, ly);
+            *reinterpret_cast<int4 *>(&rec->half) = make_int4(__double2loint(half), __double2hiint(half), -st.x, st.y);
+            rec->xy = make_int4(x, y, 0, 0);
         }
         if (P.write_flags) P.dbg_n[(size_t)y * P.flags_pitch + x] = n;
     }
@@ -239,29 +274,19 @@ __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint3
 
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
-// One NCC (ref:449-480) of the reference patch (Rlo/Rhi rows, Sr, den1) against the current image
-// at the sub-pixel position whose integer part is (ix,iy) and bilinear fractions (fx,fy).
-__device__ __forceinline__ float ncc_int_moments(const KParams &P, const uint32_t (&Rlo)[7], const uint32_t (&Rhi)[7],
-                                                 int Sr, float den1f, int ix, int iy, float fx, float fy) {
-    const uint8_t *base = P.curr + (size_t)(iy - 3) * P.curr_pitch + (ix - 3);
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - mis);
-    const unsigned sh = mis * 8u;
-    const int pitch_w = P.curr_pitch >> 2;
+// Integer moments of the 8x8 u8 block whose rows are (lo[j], hi[j]) = bytes 0..3 / 4..7.
+// Window (a,b) = columns a..a+6, rows b..b+6 of the block.
+struct BlockMoments {
+    int S00, S10, S01, S11;                                                   // window sums
+    int G0000, G1010, G0101, G1111, G0010, G0111, G0001, G1011, G0011, G1001;  // Gram sums
+};
+__device__ __forceinline__ BlockMoments block_moments(const uint32_t (&lo)[8], const uint32_t (&hi)[8]) {
     const uint32_t ONES = 0x01010101u;
-
-    // all 24 gathers first (memory-level parallelism), then the integer moments
-    uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) load_row8(wp + j * pitch_w, sh, lo[j], hi[j]);
-
-    // accumulators: t = block row 0, m = rows 1..6, b = row 7
-    int s0t = 0, s0m = 0, s0b = 0, s1t = 0, s1m = 0, s1b = 0;  // row sums, column window a=0 / a=1
-    int q0t = 0, q0m = 0, q0b = 0, q1t = 0, q1m = 0, q1b = 0;  // sums of squares
-    int ht = 0, hm = 0, hb = 0;                                // horizontal neighbour products
-    int v0 = 0, v1 = 0, d01 = 0, d10 = 0;                      // vertical / diagonal products (rows j, j+1)
-    int R00 = 0, R10 = 0, R01 = 0, R11 = 0;                    // cross sums with the reference patch
-    uint32_t p0l = 0, p0h = 0, p1l = 0, p1h = 0;               // previous row
+    int s0t = 0, s0m = 0, s0b = 0, s1t = 0, s1m = 0, s1b = 0;
+    int q0t = 0, q0m = 0, q0b = 0, q1t = 0, q1m = 0, q1b = 0;
+    int ht = 0, hm = 0, hb = 0;
+    int v0 = 0, v1 = 0, d01 = 0, d10 = 0;
+    uint32_t p0l = 0, p0h = 0, p1l = 0, p1h = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint32_t x0l = lo[j], x0h = hi[j] & 0x00FFFFFFu;                    // columns 0..6
@@ -284,55 +309,110 @@ __device__ __forceinline__ float ncc_int_moments(const KParams &P, const uint32_
             v1 = dp4(p1l, x1l, dp4(p1h, x1h, v1));
             d01 = dp4(p0l, x1l, dp4(p0h, x1h, d01));
             d10 = dp4(p1l, x0l, dp4(p1h, x0h, d10));
-            R01 = dp4(Rlo[j - 1], x0l, dp4(Rhi[j - 1], x0h, R01));
-            R11 = dp4(Rlo[j - 1], x1l, dp4(Rhi[j - 1], x1h, R11));
-        }
-        if (j < 7) {
-            R00 = dp4(Rlo[j], x0l, dp4(Rhi[j], x0h, R00));
-            R10 = dp4(Rlo[j], x1l, dp4(Rhi[j], x1h, R10));
         }
         p0l = x0l; p0h = x0h; p1l = x1l; p1h = x1h;
     }
-    // window (a,b): columns a..a+6, rows b..b+6
-    const int S00 = s0t + s0m, S01 = s0m + s0b, S10 = s1t + s1m, S11 = s1m + s1b;
-    // exact centring in int32 (all terms < 2^31)
-    const int cR00 = NCC_AREA * R00 - Sr * S00, cR10 = NCC_AREA * R10 - Sr * S10;
-    const int cR01 = NCC_AREA * R01 - Sr * S01, cR11 = NCC_AREA * R11 - Sr * S11;
-    const int G0000 = NCC_AREA * (q0t + q0m) - S00 * S00, G0101 = NCC_AREA * (q0m + q0b) - S01 * S01;
-    const int G1010 = NCC_AREA * (q1t + q1m) - S10 * S10, G1111 = NCC_AREA * (q1m + q1b) - S11 * S11;
-    const int G0010 = NCC_AREA * (ht + hm) - S00 * S10, G0111 = NCC_AREA * (hm + hb) - S01 * S11;
-    const int G0001 = NCC_AREA * v0 - S00 * S01, G1011 = NCC_AREA * v1 - S10 * S11;
-    const int G0011 = NCC_AREA * d01 - S00 * S11, G1001 = NCC_AREA * d10 - S10 * S01;
+    BlockMoments m;
+    m.S00 = s0t + s0m; m.S01 = s0m + s0b; m.S10 = s1t + s1m; m.S11 = s1m + s1b;
+    m.G0000 = q0t + q0m; m.G0101 = q0m + q0b; m.G1010 = q1t + q1m; m.G1111 = q1m + q1b;
+    m.G0010 = ht + hm; m.G0111 = hm + hb;
+    m.G0001 = v0; m.G1011 = v1; m.G0011 = d01; m.G1001 = d10;
+    return m;
+}
 
-    // FP32 combination with the bilinear weights of ref:169-172
-    const float gx = 1.0f - fx, gy = 1.0f - fy;
-    const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
-    float num = w00 * (float)cR00;
-    num = fmaf(w10, (float)cR10, num);
-    num = fmaf(w01, (float)cR01, num);
-    num = fmaf(w11, (float)cR11, num);
-    // den2 = w^T G w
-    const float g0010 = (float)G0010, g0001 = (float)G0001, g0011 = (float)G0011;
-    const float g1001 = (float)G1001, g1011 = (float)G1011, g0111 = (float)G0111;
-    float a0 = w00 * (float)G0000;
-    a0 = fmaf(w10, g0010, a0); a0 = fmaf(w01, g0001, a0); a0 = fmaf(w11, g0011, a0);
-    float a1 = w00 * g0010;
-    a1 = fmaf(w10, (float)G1010, a1); a1 = fmaf(w01, g1001, a1); a1 = fmaf(w11, g1011, a1);
-    float a2 = w00 * g0001;
-    a2 = fmaf(w10, g1001, a2); a2 = fmaf(w01, (float)G0101, a2); a2 = fmaf(w11, g0111, a2);
-    float a3 = w00 * g0011;
-    a3 = fmaf(w10, g1011, a3); a3 = fmaf(w01, g0111, a3); a3 = fmaf(w11, (float)G1111, a3);
-    float den2 = w00 * a0;
-    den2 = fmaf(w10, a1, den2); den2 = fmaf(w01, a2, den2); den2 = fmaf(w11, a3, den2);
-    den2 = fmaxf(den2, 0.0f);
-    const float dd = fmaf(den1f, den2, NCC_EPS_INT);
-    float r = rsqrtf(dd);
-    r = r * fmaf(-0.5f * dd * r, r, 1.5f);  // one Newton step: MUFU.RSQ is only ~2 ulp
-    return num * r;
+// K2m: once per current frame — the frame-only part of every possible NCC: window sum and centred
+// Gram sums of the 8x8 block at each position (x,y) = top-left tap.  A sample whose top-left tap is
+// (bx,by) needs   mom1 at (bx,by),(bx+1,by),(bx,by+1),(bx+1,by+1)  and  mom2 at (bx,by):
+//   mom1(x,y) = { S(x,y), 49*Q - S^2, 49*H - S(x,y)S(x+1,y), 49*V - S(x,y)S(x,y+1) }   (Q,H,V: squares,
+//   mom2(x,y) = { 49*D1 - S(x,y)S(x+1,y+1), 49*D2 - S(x+1,y)S(x,y+1) }                  horizontal / vertical /
+//                                                                                        diagonal neighbour products)
+__global__ void __launch_bounds__(256) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
+                                                      int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x > width - 8 || y > height - 8) return;
+    const uint8_t *base = img + (size_t)y * pitch + x;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - mis);
+    const int pw = pitch >> 2;
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) load_row8(wp + j * pw, mis * 8u, lo[j], hi[j]);
+    const BlockMoments m = block_moments(lo, hi);
+    int4 a;
+    a.x = m.S00;
+    a.y = NCC_AREA * m.G0000 - m.S00 * m.S00;
+    a.z = NCC_AREA * m.G0010 - m.S00 * m.S10;
+    a.w = NCC_AREA * m.G0001 - m.S00 * m.S01;
+    int2 b;
+    b.x = NCC_AREA * m.G0011 - m.S00 * m.S11;
+    b.y = NCC_AREA * m.G1001 - m.S10 * m.S01;
+    mom1[(size_t)y * mom_pitch + x] = a;
+    mom2[(size_t)y * mom_pitch + x] = b;
+}
+
+// One NCC (ref:449-480) of the reference patch against the current image at the sub-pixel position
+// with integer part (ix,iy) and bilinear fractions (fx,fy) (ref:167-168).
+// R0lo/R0hi: reference rows as bytes (r0..r3),(r4,r5,r6,0) — they meet block columns 0..6 (window a=0);
+// R1lo/R1hi: the same rows shifted by one byte, (0,r0,r1,r2),(r3..r6) — they meet block columns 1..7
+// (window a=1) of the SAME unshifted block words, so the block needs no per-sample byte shifts.
+// nSr = -sum r, den1 = 49*sum r^2 - (sum r)^2.
+__device__ __forceinline__ double ncc_at(const KParams &P, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
+                                         const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr, double den1,
+                                         int ix, int iy, double fx, double fy) {
+    const unsigned off = (unsigned)(iy - 3) * (unsigned)P.curr_pitch + (unsigned)(ix - 3);
+    const unsigned sh = (off & 3u) * 8u;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.curr + (size_t)(off & ~3u));
+    const int pitch_w = P.curr_pitch >> 2;
+    // gathers first (memory-level parallelism): 24 words of the block, 5 vectors of the moment table
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) load_row8(wp + j * pitch_w, sh, lo[j], hi[j]);
+    const size_t mo = (size_t)(iy - 3) * P.mom_pitch + (size_t)(ix - 3);
+    const int4 m00 = __ldg(P.mom1 + mo), m10 = __ldg(P.mom1 + mo + 1);
+    const int4 m01 = __ldg(P.mom1 + mo + P.mom_pitch), m11 = __ldg(P.mom1 + mo + P.mom_pitch + 1);
+    const int2 md = __ldg(P.mom2 + mo);
+    // cross sums with the reference patch: window (a,b) = block columns a..a+6, rows b..b+6
+    int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j > 0) {
+            R01 = dp4(R0lo[j - 1], lo[j], dp4(R0hi[j - 1], hi[j], R01));
+            R11 = dp4(R1lo[j - 1], lo[j], dp4(R1hi[j - 1], hi[j], R11));
+        }
+        if (j < 7) {
+            R00 = dp4(R0lo[j], lo[j], dp4(R0hi[j], hi[j], R00));
+            R10 = dp4(R1lo[j], lo[j], dp4(R1hi[j], hi[j], R10));
+        }
+    }
+    // exact centring in int32 (all terms < 2^31)
+    const int cR00 = NCC_AREA * R00 + nSr * m00.x, cR10 = NCC_AREA * R10 + nSr * m10.x;
+    const int cR01 = NCC_AREA * R01 + nSr * m01.x, cR11 = NCC_AREA * R11 + nSr * m11.x;
+
+    // FP64 combination with the bilinear weights of ref:169-172
+    const double gx = 1.0 - fx, gy = 1.0 - fy;
+    const double w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
+    // int -> double conversions run on the XU pipe (I2F.F64), idle otherwise
+    double num = w00 * (double)cR00;
+    num = fma(w10, (double)cR10, num);
+    num = fma(w01, (double)cR01, num);
+    num = fma(w11, (double)cR11, num);
+    // den2 = w^T G w  with G the centred Gram matrix over the windows (00,10,01,11)
+    const double g0000 = (double)m00.y, g1010 = (double)m10.y, g0101 = (double)m01.y, g1111 = (double)m11.y;
+    const double g0010 = (double)m00.z, g0111 = (double)m01.z;
+    const double g0001 = (double)m00.w, g1011 = (double)m10.w;
+    const double g0011 = (double)md.x, g1001 = (double)md.y;
+    double a0 = w00 * g0000; a0 = fma(w10, g0010, a0); a0 = fma(w01, g0001, a0); a0 = fma(w11, g0011, a0);
+    double a1 = w00 * g0010; a1 = fma(w10, g1010, a1); a1 = fma(w01, g1001, a1); a1 = fma(w11, g1011, a1);
+    double a2 = w00 * g0001; a2 = fma(w10, g1001, a2); a2 = fma(w01, g0101, a2); a2 = fma(w11, g0111, a2);
+    double a3 = w00 * g0011; a3 = fma(w10, g1011, a3); a3 = fma(w01, g0111, a3); a3 = fma(w11, g1111, a3);
+    double den2 = w00 * a0; den2 = fma(w10, a1, den2); den2 = fma(w01, a2, den2); den2 = fma(w11, a3, den2);
+    const double dd = fma(den1, den2, NCC_EPS_INT);
+    return num * rsqrt(dd);
 }
 
 // K2b: NCC over the work units.
-__global__ void __launch_bounds__(NCC_THREADS, 2) ncc_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
     const int lane = threadIdx.x & 31;
     // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
     unsigned counts[CHUNK + 1];
@@ -349,11 +429,13 @@ __global__ void __launch_bounds__(NCC_THREADS, 2) ncc_kernel(const __grid_consta
         if (lane == 0) g = atomicAdd(&P.ctrl->cursor, (unsigned)GRAB);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total) break;
-#pragma unroll 1
+        // descriptors of all GRAB/32 slices first: their latency overlaps instead of heading every slice
+        unsigned units[GRAB / 32];
+        int lens[GRAB / 32];
+#pragma unroll
         for (int sub = 0; sub < GRAB / 32; ++sub) {
             const unsigned w0 = g + sub * 32;  // warp-uniform slot base (32-aligned)
-            if (w0 >= total) break;
-            // segment of this warp (uniform): unit length L, first slot, number of units
+            // segment of this slice (uniform): unit length L, first slot, number of units
             int L = 0;
             unsigned start = 0, cnt = 0, acc = 0;
 #pragma unroll
@@ -363,53 +445,72 @@ __global__ void __launch_bounds__(NCC_THREADS, 2) ncc_kernel(const __grid_consta
                 acc += padded;
             }
             const unsigned idx = w0 - start + lane;
-            if (idx >= cnt) continue;
-            const unsigned unit = (L == CHUNK) ? P.units_full[idx] : P.units_tail[(size_t)(L - 1) * P.n_pix + idx];
+            const bool valid = (w0 < total) && (idx < cnt);
+            lens[sub] = valid ? L : 0;
+            units[sub] = 0;
+            if (valid) units[sub] = (L == CHUNK) ? __ldg(P.units_full + idx) : __ldg(P.units_tail + (size_t)(L - 1) * P.n_pix + idx);
+        }
+#pragma unroll
+        for (int sub = 0; sub < GRAB / 32; ++sub) {
+            const int L = lens[sub];
+            if (L == 0) continue;
+            const unsigned unit = units[sub];
             const int pidx = (int)(unit >> CHUNK_BITS);
             const int k0 = (int)(unit & ((1u << CHUNK_BITS) - 1u)) * CHUNK;
-            const int yl = pidx / P.wi;
-            const int x = P.border + (pidx - yl * P.wi), y = P.row_begin + yl;
+            // one 64-byte record fetch
+            const PixelRec *rec = P.rec + pidx;
+            const double2 pm = rec->pm, dir = rec->dir;
+            const int4 hv = *reinterpret_cast<const int4 *>(&rec->half);
+            const int4 xy = rec->xy;
+            const double half = __hiloint2double(hv.y, hv.x);
+            const int nSr = hv.z;
+            const double den1 = (double)hv.w;
+            const int x = xy.x, y = xy.y;
 
             // reference patch of (x,y) into registers
-            uint32_t Rlo[7], Rhi[7];
+            uint32_t R0lo[7], R0hi[7], R1lo[7], R1hi[7];
             {
-                const uint8_t *rb = P.ref + (size_t)(y - 3) * P.ref_pitch + (x - 3);
-                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rb) & 3u);
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(rb - mis);
+                const unsigned off = (unsigned)(y - 3) * (unsigned)P.ref_pitch + (unsigned)(x - 3);
+                const unsigned sh = (off & 3u) * 8u;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.ref + (size_t)(off & ~3u));
                 const int pw = P.ref_pitch >> 2;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) {
-                    load_row8(wp + j * pw, mis * 8u, Rlo[j], Rhi[j]);
-                    Rhi[j] &= 0x00FFFFFFu;
+                    uint32_t a, b;
+                    load_row8(wp + j * pw, sh, a, b);
+                    b &= 0x00FFFFFFu;
+                    R0lo[j] = a; R0hi[j] = b;
+                    R1lo[j] = a << 8; R1hi[j] = __funnelshift_l(a, b, 8);
                 }
             }
-            const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
-            const float den1f = (float)st.y;
-            const double half = P.s_half[pidx], pmx = P.s_pmx[pidx], pmy = P.s_pmy[pidx];
-            const double ex = P.s_dx[pidx], ey = P.s_dy[pidx];
 
-            float best_v = -1.0f;  // ref:430
+            double best_v = -1.0;  // ref:430
             int best_k = -1;
+            // position of the first sample; inside the loop the position of sample j+1 is computed
+            // before the NCC of sample j so its FP64 -> int chain is off the critical path
+            double sx, sy;
+            {
+                const double l = sample_l(half, P.step, k0);
+                sx = fma(l, dir.x, pm.x);  // ref:433
+                sy = fma(l, dir.y, pm.y);
+            }
 #pragma unroll 1
             for (int j = 0; j < L; ++j) {
-                const int k = k0 + j;
-                const double l = sample_l(half, P.step, k);
-                const double sx = fma(l, ex, pmx);  // ref:433
-                const double sy = fma(l, ey, pmy);
+                const double cx = sx, cy = sy;
+                {
+                    const double l = sample_l(half, P.step, k0 + j + 1);
+                    sx = fma(l, dir.x, pm.x);
+                    sy = fma(l, dir.y, pm.y);
+                }
                 // inside() ref:222-224
-                const bool ok = sx >= P.border && sy >= P.border && sx + P.border < P.width && sy + P.border <= P.height;
+                const bool ok = cx >= P.border && cy >= P.border && cx + P.border < P.width && cy + P.border <= P.height;
                 if (!ok) continue;
-                const int ix = (int)sx, iy = (int)sy;  // positive: trunc == floor
-                const float fx = (float)(sx - (double)ix), fy = (float)(sy - (double)iy);
-                const float v = ncc_int_moments(P, Rlo, Rhi, st.x, den1f, ix, iy, fx, fy);
+                const int ix = (int)cx, iy = (int)cy;  // positive: trunc == floor
+                const double v = ncc_at(P, R0lo, R0hi, R1lo, R1hi, nSr, den1, ix, iy, cx - (double)ix, cy - (double)iy);
                 ++my_evals;
-                if (v > best_v) { best_v = v; best_k = k; }  // first strict maximum ref:438-441
+                if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
-            if (best_k >= 0) {
-                const unsigned long long key = ((unsigned long long)ordered_bits(best_v) << 32) |
-                                               (unsigned long long)(0xFFFFFFFEu - (unsigned)best_k);
-                atomicMax(&P.best[pidx], key);
-            }
+            if (best_k >= 0) atomicMax(&P.best[pidx], ncc_key(best_v, best_k));
         }
     }
 #pragma unroll
@@ -439,16 +540,17 @@ __global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ 
     }
     if (active) {
         key = P.best[pidx];
-        const float best = from_ordered_bits((unsigned)(key >> 32));
-        accepted = !(best < P.ncc_thresh) && ((unsigned)key != 0xFFFFFFFFu);  // ref:443; sentinel: nothing beat -1.0
+        accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
     }
     if (accepted) {
         const double mu = P.depth[(size_t)y * P.state_pitch + x];
-        const int k = (int)(0xFFFFFFFEu - (unsigned)key);
-        const double half = P.s_half[pidx];
-        const double ex = P.s_dx[pidx], ey = P.s_dy[pidx];
+        const int k = key_index(key);
+        const PixelRec *rec = P.rec + pidx;
+        const double2 pm = rec->pm, dir = rec->dir;
+        const double half = rec->half;
+        const double ex = dir.x, ey = dir.y;
         const double l = sample_l(half, P.step, k);
-        const double cxp = fma(l, ex, P.s_pmx[pidx]), cyp = fma(l, ey, P.s_pmy[pidx]);  // pt_curr
+        const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
         // updateDepthFilter ref:482-567
         D3 f_ref{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};
         normalize3(f_ref);
@@ -487,10 +589,10 @@ __global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ 
     if (P.write_flags && in_img) {
         const size_t o = (size_t)y * P.flags_pitch + x;
         P.flags[o] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
-        P.dbg_ncc[o] = active ? from_ordered_bits((unsigned)(key >> 32)) : 0.0f;
-        const unsigned kb = ((unsigned)key == 0xFFFFFFFFu) ? 0xFFFFu : (0xFFFFFFFEu - (unsigned)key);
+        P.dbg_ncc[o] = active ? (float)key_ncc(key) : 0.0f;
+        const unsigned kb = key_has_winner(key) ? (unsigned)key_index(key) : 0xFFFFu;
         const int trips = P.dbg_n[o] & 0xFFFF;
-        P.dbg_n[o] = active ? ((trips << 16) | (int)(kb > 0xFFFEu ? 0xFFFFu : kb)) : 0;
+        P.dbg_n[o] = active ? ((trips << 16) | (int)kb) : 0;
     }
     // counters: one global atomic per warp
     const unsigned a = __popc(__ballot_sync(0xffffffffu, active));
