@@ -107,6 +107,8 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     for (int i = 0; i < 4; ++i) K.q[i] = q[i];
     for (int i = 0; i < 3; ++i) K.t[i] = t[i];
     se3_inverse(q, t, K.qi, K.ti);
+    K.ti_norm = std::sqrt(K.ti[0] * K.ti[0] + (K.ti[1] * K.ti[1] + K.ti[2] * K.ti[2]));
+    K.inv_fx = 1.0 / p.fx; K.inv_fy = 1.0 / p.fy; K.inv_step = 1.0 / p.step;
     K.curr = d_curr; K.ref = c->d_ref; K.refstat = c->d_refstat;
     K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
     K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;

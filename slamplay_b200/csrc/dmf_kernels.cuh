@@ -93,9 +93,11 @@ struct KParams {
     int write_flags;
     double ncc_thresh;
     double fx, fy, cx, cy;
+    double inv_fx, inv_fy, inv_step;  // host-side reciprocals
     double step, max_half_len, min_depth, n_sigma, min_cov, max_cov;
     double q[4], t[3];    // T_C_R (unit quaternion x,y,z,w + translation)
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
+    double ti_norm;       // |t_RC| (ref:525)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
     const uint8_t *ref;
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
@@ -135,6 +137,9 @@ __device__ __forceinline__ void normalize3(D3 &a) {  // Eigen normalize(): only 
     double z = dot3(a, a);
     if (z > 0) { double n = sqrt(z); a.x /= n; a.y /= n; a.z /= n; }
 }
+// normalize(px2cam(u,v)) ref:207-212,403: one reciprocal square root instead of sqrt + 3 divisions
+// (differs from the reference's divide-by-norm in the last ulp only)
+__device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v);
 // exact int -> double for |k| < 2^31 without the slow I2F.F64 path
 __device__ __forceinline__ double int2double_fast(int k) {
     return __hiloint2double(0x43300000, (int)((unsigned)k ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
@@ -181,6 +186,42 @@ __global__ void __launch_bounds__(256) ref_stats_kernel(const uint8_t *__restric
     stat[(size_t)y * stat_pitch + x] = make_int2(s, NCC_AREA * s2 - s * s);
 }
 
+__device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v) {
+    const double X = (u - P.cx) * P.inv_fx, Y = (v - P.cy) * P.inv_fy;
+    const double r = rsqrt(fma(X, X, fma(Y, Y, 1.0)));
+    return {X * r, Y * r, r};
+}
+
+// Epipolar search geometry of pixel (x,y) with state (mu, c2): ref:402-422.
+__device__ __forceinline__ void search_geometry(const KParams &P, int x, int y, double mu, double c2, double &pmx, double &pmy,
+                                             double &lx, double &ly, double &half) {
+    const double sigma = sqrt(c2);  // ref:377
+    const D3 f_ref = unit_ray(P, (double)x, (double)y);  // ref:402-403
+    const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
+    double d_min, d_max;
+    if (P.inverse_depth) {  // ref:407-410
+        const double inv_mu = 1.0 / mu;
+        d_min = 1.0 / (inv_mu + P.n_sigma * sigma);
+        d_max = 1.0 / (inv_mu - P.n_sigma * sigma);
+    } else {  // ref:412
+        d_min = mu - P.n_sigma * sigma;
+        d_max = mu + P.n_sigma * sigma;
+    }
+    if (d_min < P.min_depth) d_min = P.min_depth;  // ref:414
+    // cam2px ref:215-219 of the three points (one reciprocal per point)
+    const double rzm = 1.0 / fma(Rf.z, mu, P.t[2]), rz0 = 1.0 / fma(Rf.z, d_min, P.t[2]), rz1 = 1.0 / fma(Rf.z, d_max, P.t[2]);
+    pmx = fma(fma(Rf.x, mu, P.t[0]) * P.fx, rzm, P.cx);
+    pmy = fma(fma(Rf.y, mu, P.t[1]) * P.fy, rzm, P.cy);
+    const double p0x = fma(fma(Rf.x, d_min, P.t[0]) * P.fx, rz0, P.cx), p0y = fma(fma(Rf.y, d_min, P.t[1]) * P.fy, rz0, P.cy);
+    const double p1x = fma(fma(Rf.x, d_max, P.t[0]) * P.fx, rz1, P.cx), p1y = fma(fma(Rf.y, d_max, P.t[1]) * P.fy, rz1, P.cy);
+    lx = p1x - p0x; ly = p1y - p0y;  // ref:418
+    const double len2 = fma(lx, lx, ly * ly);
+    const double len = sqrt(len2);
+    half = 0.5 * len;  // ref:421
+    if (len2 > 0) { const double rl = 1.0 / len; lx *= rl; ly *= rl; }  // ref:420 (guarded normalize)
+    if (half > P.max_half_len) half = P.max_half_len;                    // ref:422
+}
+
 // ----------------------------------------------------------------------------------------
 // K2a: per-pixel setup + work-unit emission.
 __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__ KParams P) {
@@ -195,38 +236,15 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     bool active = false;
     if (in_img) {
         const double c2 = P.cov2[(size_t)y * P.state_pitch + x];
+        const double mu = P.depth[(size_t)y * P.state_pitch + x];  // issued with the cov load: one round trip
         active = !(c2 < P.min_cov || c2 > P.max_cov);  // ref:366 — NaN passes the gate
         P.best[pidx] = key_init();
         if (active) {
-            const double mu = P.depth[(size_t)y * P.state_pitch + x];
-            const double sigma = sqrt(c2);  // ref:377
-            D3 f_ref{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};  // ref:207-212
-            normalize3(f_ref);
-            const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
-            double d_min, d_max;
-            if (P.inverse_depth) {  // ref:407-410
-                const double inv_mu = 1.0 / mu;
-                d_min = 1.0 / (inv_mu + P.n_sigma * sigma);
-                d_max = 1.0 / (inv_mu - P.n_sigma * sigma);
-            } else {  // ref:412
-                d_min = mu - P.n_sigma * sigma;
-                d_max = mu + P.n_sigma * sigma;
-            }
-            if (d_min < P.min_depth) d_min = P.min_depth;  // ref:414
-            // cam2px ref:215-219 of the three points
-            const double zm = fma(Rf.z, mu, P.t[2]), z0 = fma(Rf.z, d_min, P.t[2]), z1 = fma(Rf.z, d_max, P.t[2]);
-            const double pmx = fma(Rf.x, mu, P.t[0]) * P.fx / zm + P.cx, pmy = fma(Rf.y, mu, P.t[1]) * P.fy / zm + P.cy;
-            const double p0x = fma(Rf.x, d_min, P.t[0]) * P.fx / z0 + P.cx, p0y = fma(Rf.y, d_min, P.t[1]) * P.fy / z0 + P.cy;
-            const double p1x = fma(Rf.x, d_max, P.t[0]) * P.fx / z1 + P.cx, p1y = fma(Rf.y, d_max, P.t[1]) * P.fy / z1 + P.cy;
-            double lx = p1x - p0x, ly = p1y - p0y;  // ref:418
-            const double len2 = lx * lx + ly * ly;
-            const double len = sqrt(len2);
-            double half = 0.5 * len;  // ref:421
-            if (len2 > 0) { lx /= len; ly /= len; }            // ref:420 (guarded normalize)
-            if (half > P.max_half_len) half = P.max_half_len;  // ref:422
+            double pmx, pmy, lx, ly, half;
+            search_geometry(P, x, y, mu, c2, pmx, pmy, lx, ly, half);
             // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
             if (half >= 0) {
-                n = (int)(2.0 * half / P.step) + 1;
+                n = (int)(2.0 * half * P.inv_step) + 1;
                 while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
                 while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
             }
@@ -240,28 +258,44 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
         if (P.write_flags) P.dbg_n[(size_t)y * P.flags_pitch + x] = n;
     }
 
-    // ---- emit work units (warp-cooperative, chunk-major so that adjacent slots hold adjacent pixels)
+    // ---- emit work units.  List space is claimed once per CTA and per list (thread L does the
+    // atomicAdd for list L, so its latency is paid once per CTA instead of by every warp); every warp
+    // then writes its units chunk-major so that adjacent slots hold adjacent pixels of one image row.
+    __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units)
+    __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first slot of that warp in list L
+    const int warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_full = n / CHUNK, tail = n % CHUNK;
+    const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
     const int m_full = __reduce_max_sync(0xffffffffu, n_full);
+    unsigned my_rank = 0;
+#pragma unroll
+    for (int L = 1; L < CHUNK; ++L) {
+        const unsigned bal = __ballot_sync(0xffffffffu, tail == L);
+        if (lane == L) s_cnt[warp][L] = (unsigned)__popc(bal);
+        if (tail == L) my_rank = (unsigned)__popc(bal & lt_mask);
+    }
+    if (lane == 0) s_cnt[warp][CHUNK] = (unsigned)tot_full;
+    __syncthreads();
+    if (tid >= 1 && tid <= CHUNK) {
+        unsigned pre[TILE_PIX / 32], tot = 0;
+#pragma unroll
+        for (int w = 0; w < TILE_PIX / 32; ++w) { pre[w] = tot; tot += s_cnt[w][tid]; }
+        const unsigned base = tot ? atomicAdd(&P.ctrl->count[tid], tot) : 0u;
+#pragma unroll
+        for (int w = 0; w < TILE_PIX / 32; ++w) s_base[w][tid] = base + pre[w];
+    }
+    __syncthreads();
     if (m_full > 0) {
-        const int tot = __reduce_add_sync(0xffffffffu, n_full);
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&P.ctrl->count[CHUNK], (unsigned)tot);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned base = s_base[warp][CHUNK];
         for (int j = 0; j < m_full; ++j) {
             const unsigned bal = __ballot_sync(0xffffffffu, n_full > j);
             if (n_full > j) P.units_full[base + __popc(bal & lt_mask)] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)j;
             base += __popc(bal);
         }
     }
-    const unsigned grp = __match_any_sync(0xffffffffu, tail);
-    const int leader = __ffs(grp) - 1;
-    unsigned tbase = 0;
-    if (lane == leader && tail > 0) tbase = atomicAdd(&P.ctrl->count[tail], (unsigned)__popc(grp));
-    tbase = __shfl_sync(0xffffffffu, tbase, leader);
     if (tail > 0)
-        P.units_tail[(size_t)(tail - 1) * P.n_pix + tbase + __popc(grp & lt_mask)] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)n_full;
+        P.units_tail[(size_t)(tail - 1) * P.n_pix + s_base[warp][tail] + my_rank] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)n_full;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -520,7 +554,10 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
 
 // ----------------------------------------------------------------------------------------
 // K2c: accept test + depth-filter fusion, in place.  Also re-arms the control block.
-__global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ KParams P) {
+#ifndef DMF_FUSE_MIN_BLOCKS
+#define DMF_FUSE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(const __grid_constant__ KParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
@@ -532,57 +569,60 @@ __global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ 
     }
 
     bool active = false, accepted = false;
-    double c2 = 0;
+    double c2 = 0, mu = 0;
     unsigned long long key = 0;
     if (in_img) {
         c2 = P.cov2[(size_t)y * P.state_pitch + x];
         active = !(c2 < P.min_cov || c2 > P.max_cov);  // same gate as setup_kernel: the maps are untouched in between
     }
+    double half = 0;
+    double2 pm = make_double2(0, 0), dir = make_double2(0, 0);
     if (active) {
+        // key, record and depth in one round trip (the accept rate of active pixels is > 90 %)
         key = P.best[pidx];
+        const PixelRec *rec = P.rec + pidx;
+        pm = rec->pm; dir = rec->dir; half = rec->half;
+        mu = P.depth[(size_t)y * P.state_pitch + x];
         accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
     }
     if (accepted) {
-        const double mu = P.depth[(size_t)y * P.state_pitch + x];
         const int k = key_index(key);
-        const PixelRec *rec = P.rec + pidx;
-        const double2 pm = rec->pm, dir = rec->dir;
-        const double half = rec->half;
         const double ex = dir.x, ey = dir.y;
         const double l = sample_l(half, P.step, k);
         const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
         // updateDepthFilter ref:482-567
-        D3 f_ref{((double)x - P.cx) / P.fx, ((double)y - P.cy) / P.fy, 1.0};
-        normalize3(f_ref);
-        D3 f_curr{(cxp - P.cx) / P.fx, (cyp - P.cy) / P.fy, 1.0};
-        normalize3(f_curr);
+        const D3 f_ref = unit_ray(P, (double)x, (double)y);
+        const D3 f_curr = unit_ray(P, cxp, cyp);
         const D3 t{P.ti[0], P.ti[1], P.ti[2]};
         const D3 f2 = qrot(P.qi, f_curr);
         const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
         const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
         const double a10 = -a01;
         // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
-        const double det = a00 * a11 - a01 * a10;
-        const double ans0 = (b0 * a11 - a01 * b1) / det;
-        const double ans1 = (a00 * b1 - a10 * b0) / det;
-        const D3 pe{(ans0 * f_ref.x + (t.x + ans1 * f2.x)) / 2.0, (ans0 * f_ref.y + (t.y + ans1 * f2.y)) / 2.0,
-                    (ans0 * f_ref.z + (t.z + ans1 * f2.z)) / 2.0};
+        const double rdet = 1.0 / (a00 * a11 - a01 * a10);
+        const double ans0 = (b0 * a11 - a01 * b1) * rdet;
+        const double ans1 = (a00 * b1 - a10 * b0) * rdet;
+        const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
+                    0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
         const double depth_est = sqrt(dot3(pe, pe));
-        const double t_norm = sqrt(dot3(t, t));
-        const double alpha = acos(dot3(f_ref, t) / t_norm);
-        D3 fcp{(cxp + ex - P.cx) / P.fx, (cyp + ey - P.cy) / P.fy, 1.0};
-        normalize3(fcp);
-        const D3 mt{-t.x, -t.y, -t.z};
-        const double beta_prime = acos(dot3(fcp, mt) / t_norm);
-        const double gamma = 3.14159265358979323846 - alpha - beta_prime;
-        const double p_prime = t_norm * sin(beta_prime) / sin(gamma);
+        // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
+        // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
+        // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
+        // transcendental call (|c| > 1 by rounding gives NaN on both routes).
+        const double t_norm = P.ti_norm;
+        const double rt = 1.0 / t_norm;
+        const double ca = dot3(f_ref, t) * rt;
+        const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
+        const double cb = -dot3(fcp, t) * rt;
+        const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
+        const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
         const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
         const double d_cov2 = d_cov * d_cov;
         const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
         const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
-        const double denom = c2 + d_cov2 + 1e-10;
-        const double mu_fuse = (d_cov2 * mu0 + meas) / denom;
-        const double sig_fuse = (c2 * d_cov2) / denom;
+        const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
+        const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
+        const double sig_fuse = (c2 * d_cov2) * rden;
         P.depth[(size_t)y * P.state_pitch + x] = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
         P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
     }
@@ -594,12 +634,21 @@ __global__ void __launch_bounds__(TILE_PIX) fuse_kernel(const __grid_constant__ 
         const int trips = P.dbg_n[o] & 0xFFFF;
         P.dbg_n[o] = active ? ((trips << 16) | (int)kb) : 0;
     }
-    // counters: one global atomic per warp
+    // counters: warp ballots -> shared -> ONE pair of global atomics per CTA (same-address atomics from
+    // every warp serialise in L2 and were the critical path of this kernel)
+    __shared__ unsigned s_act, s_acc;
+    if (tid == 0) { s_act = 0; s_acc = 0; }
+    __syncthreads();
     const unsigned a = __popc(__ballot_sync(0xffffffffu, active));
     const unsigned c = __popc(__ballot_sync(0xffffffffu, accepted));
     if (lane == 0) {
-        if (a) atomicAdd(&P.counters[0], (unsigned long long)a);
-        if (c) atomicAdd(&P.counters[2], (unsigned long long)c);
+        if (a) atomicAdd(&s_act, a);
+        if (c) atomicAdd(&s_acc, c);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_act) atomicAdd(&P.counters[0], (unsigned long long)s_act);
+        if (s_acc) atomicAdd(&P.counters[2], (unsigned long long)s_acc);
     }
 }
 
