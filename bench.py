@@ -56,7 +56,7 @@ class ClockSampler:
     """nvidia-smi clock / throttle-reason sampler running during the timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index: int = 0):
         self.gpu = gpu_index
@@ -67,10 +67,14 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark(self, name: str) -> None:
+        """Remember the wall-clock time of the start / end of the timed region."""
+        setattr(self, name, time.time())
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -80,13 +84,19 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        import datetime
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        t0, t1 = getattr(self, "t_begin", None), getattr(self, "t_end", None)
         for line in Path(self.path).read_text().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
+                if t0 is not None and t1 is not None:  # keep the samples taken DURING the timed region
+                    ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 - 0.05 or ts > t1 + 0.05:
+                        continue
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
@@ -99,10 +109,7 @@ class ClockSampler:
             pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": samples in the upper half of the observed power range
-        thr = min(pw) + 0.5 * (max(pw) - min(pw)) if max(pw) > min(pw) else min(pw)
-        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
                 "reasons": sorted(reasons)}
 
 
@@ -287,11 +294,13 @@ def ours(args) -> dict | None:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark("t_begin")
     ev0.record(ctx_stream)
     for _ in range(args.steps):
         one_step()
     ev1.record(ctx_stream)
     barrier()
+    sampler.mark("t_end")
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -299,6 +308,13 @@ def ours(args) -> dict | None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     cnt = sf.counters(reset=True)
+    # one extra, untimed-for-the-metric step with CUDA events around every kernel: the share and the average
+    # launch duration of the dominant kernel (ncc_kernel) for the roofline block
+    sf.filter.set_timing(True)
+    one_step()
+    ktime = sf.filter.timing(reset=True)
+    sf.filter.set_timing(False)
+    sf.counters(reset=True)
     ms_step = ms_total / args.steps
     px_updates = interior_per_frame * n_upd
     value = px_updates / (ms_step * 1e-3)
@@ -309,14 +325,17 @@ def ours(args) -> dict | None:
         act = cnt["active"] / args.steps
         acc = cnt["accepted"] / args.steps
         flops_step = FLOP_PER_NCC * ncc + FLOP_PER_ACTIVE * act + FLOP_PER_ACCEPT * acc
-        launch_ms = ms_step / n_upd  # update_fused_kernel is the only kernel of a frame
+        k_frames = max(ktime["frames"], 1)
+        ncc_launch_ms = ktime["ncc_ms"] / k_frames
+        k_total = ktime["moments_ms"] + ktime["setup_ms"] + ktime["ncc_ms"] + ktime["fuse_ms"]
+        ncc_flops_launch = FLOP_PER_NCC * ncc / n_upd / world  # algorithmic FP32 flops of one ncc_kernel launch on one GPU
         peaks = measured_peaks()
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         # compulsory HBM bytes per step: frame + cov read + depth read of active + writes of accepted
         hbm_bytes = n_upd * (w * h + 8 * interior_per_frame / world) + 8 * act + 16 * acc
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (dp4a) NCC moments, f32 NCC combine, f64 geometry / fusion",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (dp4a) NCC moments, f64 NCC combine / geometry / fusion",
             "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "frames": F, "updates_per_step": n_upd,
                        "interior_px_per_frame": interior_per_frame, "init_depth": 3.0, "init_cov2": 3.0,
@@ -325,18 +344,26 @@ def ours(args) -> dict | None:
                        "ncc_evals_per_step": ncc, "active_px_per_step": act, "accepted_per_step": acc},
             "ncc_evals_per_s": ncc / (ms_step * 1e-3),
             "roofline": {
-                "bound": "fp32-issue", "achieved": flops_step / (ms_step * 1e-3) / 1e12 / world,
+                "bound": "fp32-issue (SURVEY.md 8d: the path is neither HBM- nor tensor-bound)",
+                "kernel": "dmf::ncc_kernel", "avg_launch_ms": ncc_launch_ms,
+                "achieved": ncc_flops_launch / (ncc_launch_ms * 1e-3) / 1e12,
                 "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
-                "frac": flops_step / (ms_step * 1e-3) / 1e12 / world / FP32_PEAK_TFLOPS_NOMINAL,
-                "traffic": None, "kernel": "dmf::update_fused_kernel", "avg_launch_ms": launch_ms,
+                "frac": ncc_flops_launch / (ncc_launch_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS_NOMINAL,
+                "traffic": None,
                 "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1965 MHz); MEASURED_PEAKS.json has no FP32 figure",
-                "flop_model": "600/NCC + 150/active px + 300/accepted px (SURVEY.md 8d), per GPU",
+                "flop_model": "600 algorithmic FP32 flop per NCC evaluation (SURVEY.md 8d); the kernel itself computes the NCC from exact "
+                              "integer moments (IDP.4A + a per-frame moment table) and is bound by L1/TEX gathers, see profiles/",
+                "kernel_share_of_step": ktime["ncc_ms"] / k_total if k_total else None,
+                "kernel_ms_per_step": {k: ktime[k] for k in ("moments_ms", "setup_ms", "ncc_ms", "fuse_ms")},
+                "whole_step": {"achieved": flops_step / (ms_step * 1e-3) / 1e12 / world,
+                               "frac": flops_step / (ms_step * 1e-3) / 1e12 / world / FP32_PEAK_TFLOPS_NOMINAL,
+                               "flop_model": "600/NCC + 150/active px + 300/accepted px, per GPU"},
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / world / hbm_peak,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"},
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (n_upd + 1) ,
+            "gpu_launches": args.steps * (4 * n_upd + 1),
         }
 
     # ---- end-to-end through the public API with HOST buffers (single-process path) --------

@@ -142,6 +142,15 @@ int dmf_update_device(dmf_ctx *ctx, const uint8_t *curr_dev, size_t step,
 
 int dmf_sync(dmf_ctx *ctx);
 
+/*
+ * Optional per-kernel timing for the roofline report (bench.py): with timing enabled every update()
+ * brackets its four kernels (block moments, setup, ncc, fuse) with CUDA events on the context stream.
+ * dmf_get_timing synchronises and returns the accumulated milliseconds per kernel class and the number
+ * of frames they cover.  Off by default (the events cost ~1 % on small frames).
+ */
+int dmf_set_timing(dmf_ctx *ctx, int enable);
+int dmf_get_timing(dmf_ctx *ctx, double ms_out[4], uint64_t *frames, int reset);
+
 /* Work counters accumulated on the device; `reset` != 0 clears them after reading. Syncs. */
 int dmf_read_counters(dmf_ctx *ctx, dmf_counters *out, int reset);
 

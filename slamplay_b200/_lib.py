@@ -68,6 +68,8 @@ DMF_SYMBOLS = {
     "dmf_update": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double)]),
     "dmf_update_device": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double), _vp]),
     "dmf_sync": (C.c_int, [_vp]),
+    "dmf_set_timing": (C.c_int, [_vp, C.c_int]),
+    "dmf_get_timing": (C.c_int, [_vp, _P(C.c_double), _P(C.c_uint64), C.c_int]),
     "dmf_read_counters": (C.c_int, [_vp, _P(DmfCounters), C.c_int]),
     "dmf_enable_flags": (C.c_int, [_vp, C.c_int]),
     "dmf_download_flags": (C.c_int, [_vp, _vp, C.c_size_t]),

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -43,6 +44,12 @@ struct dmf_ctx_impl {
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
     int2 *d_mom2 = nullptr;
     int n_pix = 0, ncc_grid = 0;
+    // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
+    bool timing_on = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double timing_ms[4] = {0, 0, 0, 0};
+    unsigned long long timing_frames = 0;
     bool have_ref = false, flags_on = false, have_truth = false;
     unsigned long long frames = 0;
     unsigned long long frame_idx = 0;
@@ -122,10 +129,26 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
         dim3 mgrid((p.width - 7 + 31) / 32, (p.height - 7 + 7) / 8);
+        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (c->timing_on) {
+            for (int i = 0; i < 5; ++i) {
+                if (c->ev_used == c->ev_pool.size()) {
+                    cudaEvent_t e;
+                    CU(cudaEventCreate(&e));
+                    c->ev_pool.push_back(e);
+                }
+                ev[i] = c->ev_pool[c->ev_used++];
+            }
+            CU(cudaEventRecord(ev[0], c->stream));
+        }
         dmf::moments_kernel<<<mgrid, 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width);
+        if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
+        if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
         dmf::fuse_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
         CU(cudaGetLastError());
     }
     c->frames++;
@@ -265,6 +288,7 @@ void dmf_destroy(dmf_ctx *ctx) {
         if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
     }
     if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2);
@@ -425,6 +449,31 @@ int dmf_read_counters(dmf_ctx *c, dmf_counters *out, int reset) {
     out->interior = c->frames * (unsigned long long)(c->row_end - c->row_begin) * (unsigned long long)(c->prm.width - 2 * c->prm.border);
     out->active = h[0]; out->ncc_evals = h[1]; out->accepted = h[2];
     if (reset) c->frames = 0;
+    return DMF_OK;
+}
+
+int dmf_set_timing(dmf_ctx *c, int enable) {
+    if (!c) return fail(c, DMF_ERR_INVALID, "dmf_set_timing: NULL context");
+    c->timing_on = enable != 0;
+    return DMF_OK;
+}
+
+int dmf_get_timing(dmf_ctx *c, double ms_out[4], uint64_t *frames, int reset) {
+    if (!c || !ms_out || !frames) return fail(c, DMF_ERR_INVALID, "dmf_get_timing: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 4 < c->ev_used + 1 && i + 4 < c->ev_pool.size() + 1 && i + 5 <= c->ev_used; i += 5) {
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->ev_pool[i + k], c->ev_pool[i + k + 1]));
+            c->timing_ms[k] += ms;
+        }
+        c->timing_frames++;
+    }
+    c->ev_used = 0;
+    for (int k = 0; k < 4; ++k) ms_out[k] = c->timing_ms[k];
+    *frames = c->timing_frames;
+    if (reset) { for (int k = 0; k < 4; ++k) c->timing_ms[k] = 0; c->timing_frames = 0; }
     return DMF_OK;
 }
 

@@ -166,6 +166,16 @@ class DepthFilter:
         self._ck(self._lib.dmf_read_counters(self._ctx, C.byref(out), int(reset)), "dmf_read_counters")
         return out.as_dict()
 
+    def set_timing(self, on: bool = True) -> None:
+        self._ck(self._lib.dmf_set_timing(self._ctx, int(on)), "dmf_set_timing")
+
+    def timing(self, reset: bool = False) -> dict:
+        """Accumulated per-kernel milliseconds {moments, setup, ncc, fuse} and the frames they cover."""
+        ms = (C.c_double * 4)()
+        n = C.c_uint64()
+        self._ck(self._lib.dmf_get_timing(self._ctx, ms, C.byref(n), int(reset)), "dmf_get_timing")
+        return {"moments_ms": ms[0], "setup_ms": ms[1], "ncc_ms": ms[2], "fuse_ms": ms[3], "frames": int(n.value)}
+
     def enable_flags(self, on: bool = True) -> None:
         self._ck(self._lib.dmf_enable_flags(self._ctx, int(on)), "dmf_enable_flags")
 
