@@ -311,10 +311,19 @@ def ours(args) -> dict | None:
     # one extra, untimed-for-the-metric step with CUDA events around every kernel: the share and the average
     # launch duration of the dominant kernel (ncc_kernel) for the roofline block
     sf.filter.set_timing(True)
+    t_host0 = time.perf_counter()
     one_step()
+    t_enqueue = time.perf_counter() - t_host0  # host time to enqueue + finish one instrumented step
     ktime = sf.filter.timing(reset=True)
     sf.filter.set_timing(False)
     sf.counters(reset=True)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ktime["moments_ms"], ktime["setup_ms"], ktime["ncc_ms"], ktime["fuse_ms"], t_enqueue * 1e3],
+                            dtype=torch.float64, device=device)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 2) for v in t.tolist()] for t in allr]
     ms_step = ms_total / args.steps
     px_updates = interior_per_frame * n_upd
     value = px_updates / (ms_step * 1e-3)
@@ -355,6 +364,7 @@ def ours(args) -> dict | None:
                               "integer moments (IDP.4A + a per-frame moment table) and is bound by L1/TEX gathers, see profiles/",
                 "kernel_share_of_step": ktime["ncc_ms"] / k_total if k_total else None,
                 "kernel_ms_per_step": {k: ktime[k] for k in ("moments_ms", "setup_ms", "ncc_ms", "fuse_ms")},
+                "per_rank_ms[moments,setup,ncc,fuse,host_step]": per_rank,
                 "whole_step": {"achieved": flops_step / (ms_step * 1e-3) / 1e12 / world,
                                "frac": flops_step / (ms_step * 1e-3) / 1e12 / world / FP32_PEAK_TFLOPS_NOMINAL,
                                "flop_model": "600/NCC + 150/active px + 300/accepted px, per GPU"},
@@ -366,10 +376,14 @@ def ours(args) -> dict | None:
             "gpu_launches": args.steps * (4 * n_upd + 1),
         }
 
-    # ---- end-to-end through the public API with HOST buffers (single-process path) --------
-    if rank == 0 and not args.no_e2e:
-        e2e = e2e_run(args, seq, frames, pitch, torch, device)
-        result["e2e"] = e2e
+    # ---- end-to-end through the public API with HOST buffers ---------------------------------
+    if not args.no_e2e:
+        if world == 1:
+            result["e2e"] = e2e_run(args, seq, frames, pitch, torch, device)
+        else:
+            e2e = e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, poses_all)
+            if rank == 0:
+                result["e2e"] = e2e
     if world > 1:
         dist.barrier()
 
@@ -423,6 +437,47 @@ def e2e_run(args, seq, frames, pitch, torch, device) -> dict:
     interior = (h - 2 * p.border) * (w - 2 * p.border) * (F - 1)
     return {"value": interior / dt, "unit": UNIT, "h2d_bytes_per_step": (F - 1) * h * w, "d2h_bytes_per_step": 16 * h * w,
             "ms_per_step": dt * 1e3, "api": "DepthFilter.update (dmf_update, pinned host frames) + download_state"}
+
+
+def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, poses_all) -> dict:
+    """N > 1: rank 0 holds the frames in pinned host memory; per update H2D on rank 0 -> NCCL broadcast ->
+    band update on every rank; per step gather of the bands and D2H of both maps on rank 0."""
+    p = seq.params
+    h, w = seq.shape
+    F = seq.n_frames
+    host = None
+    if rank == 0:
+        host = torch.empty((F, h, w), dtype=torch.uint8, pin_memory=True)
+        host.copy_(frames[:, :, :w])
+        out_d = torch.empty((h, w), dtype=torch.float64, pin_memory=True)
+        out_c = torch.empty((h, w), dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step():
+        sf.fill_state(3.0, 3.0)
+        poses = sf.broadcast_poses(poses_all if rank == 0 else None)
+        for i in range(1, F):
+            sf.update_host(host[i] if rank == 0 else None, poses[i])
+        res = sf.gather_state()
+        if rank == 0:
+            out_d.copy_(res[0], non_blocking=True)
+            out_c.copy_(res[1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([dt], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    interior = (h - 2 * p.border) * (w - 2 * p.border) * (F - 1)
+    return {"value": interior / dt, "unit": UNIT, "h2d_bytes_per_step": (F - 1) * h * w, "d2h_bytes_per_step": 16 * h * w,
+            "ms_per_step": dt * 1e3, "api": "ShardedDepthFilter.update_host (pinned host frames on rank 0, NCCL broadcast) + gather_state + D2H"}
 
 
 def cpu_baseline_and_parity(args, seq, frames, sf, torch) -> dict:

@@ -97,6 +97,16 @@ int dmf_default_params(dmf_params *p, int width, int height, int inverse_depth);
  * dmf_destroy().
  */
 int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out);
+/*
+ * Block-cyclic row ownership for multi-GPU runs (SURVEY.md 8e "fallback if contiguous bands do not
+ * balance"): the interior rows are cut into blocks of `block_rows` rows, dealt round-robin to `n_parts`
+ * contexts; this context is number `part`.  Convergence varies smoothly down the image, so interleaved
+ * blocks give every GPU the same mix of short and long epipolar searches.  Upload / download move the
+ * owned rows only.  dmf_get_rows lists the owned image rows in local order (rows_out may be NULL to
+ * query the count).
+ */
+int dmf_create_cyclic(const dmf_params *params, int device, int block_rows, int n_parts, int part, dmf_ctx **out);
+int dmf_get_rows(const dmf_ctx *ctx, int *rows_out, int capacity, int *n_rows);
 void dmf_destroy(dmf_ctx *ctx);
 
 /* Geometry of the context. */

@@ -57,6 +57,8 @@ DMF_SYMBOLS = {
     "dmf_last_error": (C.c_char_p, [_vp]),
     "dmf_default_params": (C.c_int, [_P(DmfParams), C.c_int, C.c_int, C.c_int]),
     "dmf_create": (C.c_int, [_P(DmfParams), C.c_int, C.c_int, C.c_int, _P(_vp)]),
+    "dmf_create_cyclic": (C.c_int, [_P(DmfParams), C.c_int, C.c_int, C.c_int, C.c_int, _P(_vp)]),
+    "dmf_get_rows": (C.c_int, [_vp, _P(C.c_int), C.c_int, _P(C.c_int)]),
     "dmf_destroy": (None, [_vp]),
     "dmf_get_params": (C.c_int, [_vp, _P(DmfParams)]),
     "dmf_get_band": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int)]),

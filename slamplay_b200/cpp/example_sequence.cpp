@@ -39,8 +39,8 @@ int main(int argc, char **argv) {
         double s = 0; long n = 0;
         for (int y = p.border; y < height - p.border; y++)
             for (int x = p.border; x < width - p.border; x++)
-                if (cov_buf[size_t(y) * width + x] < 2e-2) { s += depth_buf[size_t(y) * width + x]; n++; }
-        std::printf("*** loop %d ***  pixels with cov2 < 2e-2: %ld, mean depth %.4f\n", index, n, n ? s / n : 0.0);
+                if (cov_buf[size_t(y) * width + x] < 0.5) { s += depth_buf[size_t(y) * width + x]; n++; }
+        std::printf("*** loop %d ***  pixels with cov2 < 0.5: %ld, mean depth %.4f\n", index, n, n ? s / n : 0.0);
     }
     return 0;
 }

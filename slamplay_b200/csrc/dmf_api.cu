@@ -18,8 +18,11 @@ thread_local std::string g_err;
 struct dmf_ctx_impl {
     dmf_params prm{};
     int device = 0;
-    int row_begin = 0, row_end = 0;  // interior rows owned (clamped)
-    int band_lo = 0, band_hi = 0;    // rows transferred by upload/download (as requested by the caller)
+    // rows owned: local row rl -> image row  row0 + ((rl / blk) * cyc + ph) * blk + rl % blk
+    int row0 = 0, blk = 1, cyc = 1, ph = 0, n_rows = 0;
+    std::vector<std::pair<int, int>> spans;     // owned interior rows as ascending [y0, y1) intervals
+    std::vector<std::pair<int, int>> io_spans;  // rows moved by upload / download (spans, plus border rows a contiguous band asked for)
+    uint8_t *d_row_need = nullptr;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // images
     uint8_t *d_ref = nullptr;
@@ -105,7 +108,8 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     dmf::KParams K{};
     const dmf_params &p = c->prm;
     K.width = p.width; K.height = p.height; K.border = p.border;
-    K.row_begin = c->row_begin; K.row_end = c->row_end;
+    K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows;
+    K.row_need = c->d_row_need;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
     K.ncc_thresh = p.ncc_thresh;
     K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
@@ -125,7 +129,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.rec = c->d_rec;
     K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width;
     K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.ctrl = c->d_ctrl;
-    const int rows = c->row_end - c->row_begin;
+    const int rows = c->n_rows;
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
         dim3 mgrid((p.width - 7 + 31) / 32, (p.height - 7 + 7) / 8);
@@ -141,9 +145,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             }
             CU(cudaEventRecord(ev[0], c->stream));
         }
-        dmf::moments_kernel<<<mgrid, 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width);
-        if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
+        dmf::moments_kernel<<<mgrid, 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_row_need);
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
@@ -189,7 +193,8 @@ int dmf_default_params(dmf_params *p, int width, int height, int inverse_depth) 
     return DMF_OK;
 }
 
-int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out) {
+static int create_common(const dmf_params *params, int device, int row_begin, int row_end, int block_rows, int n_parts,
+                         int part, dmf_ctx **out) {
     dmf_ctx_impl *c = nullptr;
     if (!out) return fail(c, DMF_ERR_INVALID, "dmf_create: out is NULL");
     *out = nullptr;
@@ -197,6 +202,8 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     if (check_params(params, why)) return fail(c, DMF_ERR_INVALID, "dmf_create: " + why);
     if (row_begin < 0 || row_end > params->height || row_begin > row_end)
         return fail(c, DMF_ERR_INVALID, "dmf_create: need 0 <= row_begin <= row_end <= height");
+    if (block_rows < 1 || n_parts < 1 || part < 0 || part >= n_parts)
+        return fail(c, DMF_ERR_INVALID, "dmf_create_cyclic: need block_rows >= 1 and 0 <= part < n_parts");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -213,10 +220,24 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     c = ctx;
     c->prm = *params;
     c->device = device;
-    c->band_lo = row_begin; c->band_hi = row_end;
-    c->row_begin = row_begin < params->border ? params->border : row_begin;
-    c->row_end = row_end > params->height - params->border ? params->height - params->border : row_end;
-    if (c->row_end < c->row_begin) c->row_end = c->row_begin;
+    {
+        const int lo = params->border, hi = params->height - params->border;
+        if (n_parts == 1) {  // contiguous band
+            int y0 = row_begin < lo ? lo : row_begin, y1 = row_end > hi ? hi : row_end;
+            if (y1 < y0) y1 = y0;
+            c->row0 = y0; c->blk = (y1 - y0) > 0 ? (y1 - y0) : 1; c->cyc = 1; c->ph = 0; c->n_rows = y1 - y0;
+            if (y1 > y0) c->spans.push_back({y0, y1});
+            if (row_end > row_begin) c->io_spans.push_back({row_begin, row_end});
+        } else {             // block-cyclic: blocks of block_rows interior rows dealt round-robin
+            c->row0 = lo; c->blk = block_rows; c->cyc = n_parts; c->ph = part; c->n_rows = 0;
+            for (int b = part; lo + b * block_rows < hi; b += n_parts) {
+                const int y0 = lo + b * block_rows, y1 = (y0 + block_rows < hi) ? y0 + block_rows : hi;
+                c->spans.push_back({y0, y1});
+                c->n_rows += y1 - y0;
+            }
+            c->io_spans = c->spans;
+        }
+    }
     const size_t W = params->width, H = params->height;
     c->img_pitch = (int)((W + 15) / 16 * 16);
 #define CUX(call)                                                                                         \
@@ -243,6 +264,8 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     CUX(cudaMalloc(&c->d_depth, W * H * sizeof(double)));
     CUX(cudaMalloc(&c->d_cov2, W * H * sizeof(double)));
     CUX(cudaMalloc(&c->d_flags, W * H));
+    CUX(cudaMalloc(&c->d_row_need, H));
+    CUX(cudaMemsetAsync(c->d_row_need, 0, H, c->stream));
     CUX(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
     CUX(cudaMalloc(&c->d_eval, sizeof(double)));
     CUX(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
@@ -252,7 +275,7 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     CUX(cudaMemsetAsync(c->d_cov2, 0, W * H * sizeof(double), c->stream));
     {
         // scratch of the setup -> ncc -> fuse pipeline
-        c->n_pix = (int)((W - 2 * (size_t)params->border) * (size_t)(c->row_end - c->row_begin));
+        c->n_pix = (int)((W - 2 * (size_t)params->border) * (size_t)c->n_rows);
         const size_t np = c->n_pix > 0 ? (size_t)c->n_pix : 1;
         const int n_max = (int)(2.0 * params->max_half_len / params->step) + 2;  // trip-count bound of ref:432
         const size_t max_full = (size_t)(n_max / dmf::CHUNK) + 1;
@@ -275,6 +298,24 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
     return DMF_OK;
 }
 
+int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out) {
+    return create_common(params, device, row_begin, row_end, 1, 1, 0, out);
+}
+
+int dmf_create_cyclic(const dmf_params *params, int device, int block_rows, int n_parts, int part, dmf_ctx **out) {
+    return create_common(params, device, 0, params ? params->height : 0, block_rows, n_parts, part, out);
+}
+
+int dmf_get_rows(const dmf_ctx *ctx, int *rows_out, int capacity, int *n_rows) {
+    if (!ctx || !n_rows) return fail(nullptr, DMF_ERR_INVALID, "dmf_get_rows: NULL argument");
+    int n = 0;
+    for (const auto &sp : ctx->spans)
+        for (int y = sp.first; y < sp.second; ++y, ++n)
+            if (rows_out && n < capacity) rows_out[n] = y;
+    *n_rows = n;
+    return DMF_OK;
+}
+
 void dmf_destroy(dmf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -292,6 +333,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2);
+    cudaFree(ctx->d_row_need);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -306,7 +348,8 @@ int dmf_get_params(const dmf_ctx *ctx, dmf_params *out) {
 
 int dmf_get_band(const dmf_ctx *ctx, int *row_begin, int *row_end) {
     if (!ctx || !row_begin || !row_end) return fail(nullptr, DMF_ERR_INVALID, "dmf_get_band: NULL argument");
-    *row_begin = ctx->row_begin; *row_end = ctx->row_end;
+    *row_begin = ctx->spans.empty() ? ctx->row0 : ctx->spans.front().first;
+    *row_end = ctx->spans.empty() ? ctx->row0 : ctx->spans.back().second;
     return DMF_OK;
 }
 
@@ -351,8 +394,8 @@ int dmf_upload_state(dmf_ctx *c, const double *depth, size_t depth_step, const d
     const size_t rowb = (size_t)c->prm.width * sizeof(double);
     if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_upload_state: step < width*8");
     CU(cudaSetDevice(c->device));
-    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
-    if (rows > 0) {
+    for (const auto &sp : c->io_spans) {
+        const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync(c->d_depth + (size_t)y0 * c->prm.width, rowb, (const char *)depth + (size_t)y0 * depth_step, depth_step, rowb, rows, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpy2DAsync(c->d_cov2 + (size_t)y0 * c->prm.width, rowb, (const char *)cov2 + (size_t)y0 * cov2_step, cov2_step, rowb, rows, cudaMemcpyHostToDevice, c->stream));
     }
@@ -365,8 +408,8 @@ int dmf_download_state(dmf_ctx *c, double *depth, size_t depth_step, double *cov
     const size_t rowb = (size_t)c->prm.width * sizeof(double);
     if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_download_state: step < width*8");
     CU(cudaSetDevice(c->device));
-    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
-    if (rows > 0) {
+    for (const auto &sp : c->io_spans) {
+        const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync((char *)depth + (size_t)y0 * depth_step, depth_step, c->d_depth + (size_t)y0 * c->prm.width, rowb, rowb, rows, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpy2DAsync((char *)cov2 + (size_t)y0 * cov2_step, cov2_step, c->d_cov2 + (size_t)y0 * c->prm.width, rowb, rowb, rows, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -446,7 +489,7 @@ int dmf_read_counters(dmf_ctx *c, dmf_counters *out, int reset) {
     if (reset) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     out->frames = c->frames;
-    out->interior = c->frames * (unsigned long long)(c->row_end - c->row_begin) * (unsigned long long)(c->prm.width - 2 * c->prm.border);
+    out->interior = c->frames * (unsigned long long)c->n_rows * (unsigned long long)(c->prm.width - 2 * c->prm.border);
     out->active = h[0]; out->ncc_evals = h[1]; out->accepted = h[2];
     if (reset) c->frames = 0;
     return DMF_OK;
@@ -495,9 +538,10 @@ int dmf_download_flags(dmf_ctx *c, uint8_t *flags_host, size_t step) {
     if (!c || !flags_host) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: NULL argument");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: step < width");
     CU(cudaSetDevice(c->device));
-    const int y0 = c->band_lo, rows = c->band_hi - c->band_lo;
-    if (rows > 0)
+    for (const auto &sp : c->io_spans) {
+        const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync(flags_host + (size_t)y0 * step, step, c->d_flags + (size_t)y0 * c->prm.width, c->prm.width, c->prm.width, rows, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     return DMF_OK;
 }
@@ -556,9 +600,9 @@ int dmf_evaluate_depth(dmf_ctx *c, double max_variance, double *sum_sq, uint64_t
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_eval, 0, sizeof(double), c->stream));
     CU(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
-    if (c->row_end > c->row_begin) {
+    for (const auto &sp : c->spans) {
         dmf::evaluate_depth_kernel<<<148 * 2, 256, 0, c->stream>>>(c->d_truth, c->d_depth, c->d_cov2, c->prm.width, c->prm.border,
-                                                                   c->prm.width - c->prm.border, c->row_begin, c->row_end, max_variance,
+                                                                   c->prm.width - c->prm.border, sp.first, sp.second, max_variance,
                                                                    c->d_eval, c->d_counters + 3);
         CU(cudaGetLastError());
     }
@@ -576,8 +620,8 @@ int dmf_variance_mask(dmf_ctx *c, double max_variance, uint8_t *mask_host, size_
     CU(cudaSetDevice(c->device));
     const int W = c->prm.width;
     if (!c->d_mask) CU(cudaMalloc(&c->d_mask, (size_t)W * c->prm.height));
-    const int y0 = c->band_lo, y1 = c->band_hi;
-    if (y1 > y0) {
+    for (const auto &sp : c->io_spans) {
+        const int y0 = sp.first, y1 = sp.second;
         dim3 blk(64, 4), grid((W + 63) / 64, (y1 - y0 + 3) / 4);
         dmf::variance_mask_kernel<<<grid, blk, 0, c->stream>>>(c->d_cov2, W, W, y0, y1, max_variance, c->d_mask, W);
         CU(cudaGetLastError());

@@ -86,9 +86,13 @@ static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 
 struct KParams {
     int width, height, border;
-    int row_begin, row_end;  // interior rows owned by this context
+    // Rows owned by this context: local row rl in [0, n_rows) is image row
+    //   y = row0 + ((rl / blk) * cyc + ph) * blk + rl % blk
+    // (block-cyclic: blocks of `blk` rows dealt round-robin to `cyc` contexts, this one being `ph`;
+    //  a contiguous band is blk = n_rows, cyc = 1, ph = 0).
+    int row0, blk, cyc, ph, n_rows;
     int wi;                  // width - 2*border
-    int n_pix;               // interior pixels of the band = wi * (row_end - row_begin)
+    int n_pix;               // interior pixels owned = wi * n_rows
     int inverse_depth;
     int write_flags;
     double ncc_thresh;
@@ -111,6 +115,7 @@ struct KParams {
     unsigned int *units_full;                      // units of length CHUNK
     unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
     Ctrl *ctrl;
+    uint8_t *row_need;                             // [height/8 + 1]: 8-row groups of the moment table some sample reads
     uint8_t *flags;
     float *dbg_ncc;  // with write_flags: best NCC per active pixel (rounded to f32)
     int *dbg_n;      // with write_flags: (trip count << 16) | winning iteration (0xFFFF: none)
@@ -143,6 +148,10 @@ __device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v);
 // exact int -> double for |k| < 2^31 without the slow I2F.F64 path
 __device__ __forceinline__ double int2double_fast(int k) {
     return __hiloint2double(0x43300000, (int)((unsigned)k ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+__device__ __forceinline__ int row_of(const KParams &P, int rl) {
+    const int b = rl / P.blk;
+    return P.row0 + (b * P.cyc + P.ph) * P.blk + (rl - b * P.blk);
 }
 // sample position parameter of iteration k of the loop ref:432, l_k = -half + step*k
 __device__ __forceinline__ double sample_l(double half, double step, int k) {
@@ -228,12 +237,14 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
-    const int y = P.row_begin + blockIdx.y * TILE_H + (tid / TILE_W);
-    const bool in_img = (x < P.width - P.border) && (y < P.row_end);
-    const int pidx = (y - P.row_begin) * P.wi + (x - P.border);
+    const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
+    const bool in_img = (x < P.width - P.border) && (rl < P.n_rows);
+    const int y = row_of(P, rl);
+    const int pidx = rl * P.wi + (x - P.border);
 
     int n = 0;
     bool active = false;
+    int need_lo = 0x7fffffff, need_hi = -1;  // moment-table rows this pixel's samples read
     if (in_img) {
         const double c2 = P.cov2[(size_t)y * P.state_pitch + x];
         const double mu = P.depth[(size_t)y * P.state_pitch + x];  // issued with the cov load: one round trip
@@ -248,6 +259,13 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
                 while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
                 while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
             }
+            if (n > 0) {
+                // sample rows span pmy -/+ half*ly; a sample with integer row iy reads table rows iy-3, iy-2
+                const double ya = fma(-half, ly, pmy), yb = fma(half, ly, pmy);
+                const double ylo = fmin(ya, yb), yhi = fmax(ya, yb);
+                need_lo = max((int)fmax(ylo, (double)P.border) - 3, 0);
+                need_hi = min((int)fmin(yhi, (double)(P.height - P.border)) - 2, P.height - 1);
+            }
             const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
             PixelRec *rec = P.rec + pidx;  // four 16-byte vector stores
             rec->pm = make_double2(pmx, pmy);
@@ -261,9 +279,16 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     // ---- emit work units.  List space is claimed once per CTA and per list (thread L does the
     // atomicAdd for list L, so its latency is paid once per CTA instead of by every warp); every warp
     // then writes its units chunk-major so that adjacent slots hold adjacent pixels of one image row.
+    __shared__ int s_need_lo, s_need_hi;                   // moment-table rows the CTA's samples read
     __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units)
     __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first slot of that warp in list L
     const int warp = tid >> 5;
+    if (tid == 0) { s_need_lo = 0x7fffffff; s_need_hi = -1; }
+    __syncthreads();
+    {
+        const int lo = __reduce_min_sync(0xffffffffu, need_lo), hi = __reduce_max_sync(0xffffffffu, need_hi);
+        if (lane == 0 && hi >= lo) { atomicMin(&s_need_lo, lo); atomicMax(&s_need_hi, hi); }
+    }
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_full = n / CHUNK, tail = n % CHUNK;
     const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
@@ -286,6 +311,9 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
         for (int w = 0; w < TILE_PIX / 32; ++w) s_base[w][tid] = base + pre[w];
     }
     __syncthreads();
+    // mark the 8-row groups of the moment table this CTA's samples read (moments_kernel skips the others)
+    if (s_need_hi >= s_need_lo)
+        for (int g = (s_need_lo >> 3) + tid; g <= (s_need_hi >> 3); g += TILE_PIX) P.row_need[g] = 1;
     if (m_full > 0) {
         unsigned base = s_base[warp][CHUNK];
         for (int j = 0; j < m_full; ++j) {
@@ -361,10 +389,12 @@ __device__ __forceinline__ BlockMoments block_moments(const uint32_t (&lo)[8], c
 //   mom2(x,y) = { 49*D1 - S(x,y)S(x+1,y+1), 49*D2 - S(x+1,y)S(x,y+1) }                  horizontal / vertical /
 //                                                                                        diagonal neighbour products)
 __global__ void __launch_bounds__(256) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
-                                                      int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch) {
+                                                      int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch,
+                                                      const uint8_t *__restrict__ row_need) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x > width - 8 || y > height - 8) return;
+    if (!row_need[blockIdx.y]) return;  // no sample of this frame reads these 8 table rows (CTA-uniform)
     const uint8_t *base = img + (size_t)y * pitch + x;
     const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - mis);
@@ -561,11 +591,15 @@ __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(con
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
-    const int y = P.row_begin + blockIdx.y * TILE_H + (tid / TILE_W);
-    const bool in_img = (x < P.width - P.border) && (y < P.row_end);
-    const int pidx = (y - P.row_begin) * P.wi + (x - P.border);
+    const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
+    const bool in_img = (x < P.width - P.border) && (rl < P.n_rows);
+    const int y = row_of(P, rl);
+    const int pidx = rl * P.wi + (x - P.border);
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) {
         reinterpret_cast<unsigned *>(P.ctrl)[tid] = 0;  // ncc_kernel of this frame is done (stream order)
+    }
+    if (blockIdx.y == 0) {  // re-arm the row flags for the next frame
+        for (int r = blockIdx.x * TILE_PIX + tid; r < P.height / 8 + 1; r += gridDim.x * TILE_PIX) P.row_need[r] = 0;
     }
 
     bool active = false, accepted = false;

@@ -73,12 +73,18 @@ class DepthFilter:
     """Resident depth-filter context (one per GPU / row band)."""
 
     def __init__(self, params: Optional[DmfParams] = None, *, width: int = 640, height: int = 480,
-                 device: int = 0, rows: Optional[Tuple[int, int]] = None, inverse_depth: bool = False):
+                 device: int = 0, rows: Optional[Tuple[int, int]] = None, inverse_depth: bool = False,
+                 cyclic: Optional[Tuple[int, int, int]] = None):
+        """rows=(r0, r1): contiguous band; cyclic=(block_rows, n_parts, part): block-cyclic row ownership."""
         self._lib = _lib.load_dmf()
         self.params = params.copy() if params is not None else default_params(width, height, inverse_depth)
         r0, r1 = rows if rows is not None else (0, self.params.height)
         self._ctx = C.c_void_p()
-        rc = self._lib.dmf_create(C.byref(self.params), int(device), int(r0), int(r1), C.byref(self._ctx))
+        if cyclic is not None:
+            rc = self._lib.dmf_create_cyclic(C.byref(self.params), int(device), int(cyclic[0]), int(cyclic[1]), int(cyclic[2]),
+                                             C.byref(self._ctx))
+        else:
+            rc = self._lib.dmf_create(C.byref(self.params), int(device), int(r0), int(r1), C.byref(self._ctx))
         if rc != 0:
             msg = self._lib.dmf_last_error(None).decode()
             self._ctx = C.c_void_p()
@@ -198,6 +204,14 @@ class DepthFilter:
         a, b = C.c_int(), C.c_int()
         self._ck(self._lib.dmf_get_band(self._ctx, C.byref(a), C.byref(b)), "dmf_get_band")
         return a.value, b.value
+
+    def owned_rows(self) -> np.ndarray:
+        """Image rows this context updates, in local order."""
+        n = C.c_int()
+        self._ck(self._lib.dmf_get_rows(self._ctx, None, 0, C.byref(n)), "dmf_get_rows")
+        out = (C.c_int * max(n.value, 1))()
+        self._ck(self._lib.dmf_get_rows(self._ctx, out, n.value, C.byref(n)), "dmf_get_rows")
+        return np.array(out[: n.value], dtype=np.int64)
 
     def device_state(self) -> Tuple[int, int, int]:
         d, c, pitch = C.c_void_p(), C.c_void_p(), C.c_size_t()

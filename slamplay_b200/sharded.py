@@ -36,6 +36,18 @@ def band_rows(height: int, border: int, world: int, rank: int) -> Tuple[int, int
     return start, stop
 
 
+def cyclic_rows(height: int, border: int, block_rows: int, world: int, rank: int) -> np.ndarray:
+    """Interior rows of `rank` under block-cyclic ownership (same rule as dmf_create_cyclic)."""
+    lo, hi = border, height - border
+    rows = []
+    b = rank
+    while lo + b * block_rows < hi:
+        y0 = lo + b * block_rows
+        rows.extend(range(y0, min(y0 + block_rows, hi)))
+        b += world
+    return np.array(rows, dtype=np.int64)
+
+
 class _DevArray:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
 
@@ -47,7 +59,11 @@ class _DevArray:
 class ShardedDepthFilter:
     """Depth filter whose state is split into row bands over the ranks of a process group."""
 
-    def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 3):
+    def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 3,
+                 layout: str = "cyclic", block_rows: int = 32):
+        """layout "cyclic" (default): blocks of `block_rows` interior rows dealt round-robin to the ranks —
+        convergence varies smoothly down the image, so this balances the per-rank work; "bands": one
+        contiguous band per rank (SURVEY.md 8e first choice; measured 4x imbalance on the 4K sequence)."""
         import torch
         import torch.distributed as dist
 
@@ -56,6 +72,8 @@ class ShardedDepthFilter:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = params
+        self.layout = layout if self.world > 1 else "bands"
+        self.block_rows = block_rows
         r0, r1 = band_rows(params.height, params.border, self.world, self.rank)
         self.rows = (r0, r1)
         self.pitch = (params.width + 15) // 16 * 16
@@ -70,7 +88,10 @@ class ShardedDepthFilter:
     def _attach(self, device, n_ring) -> None:
         torch = self.torch
         self.device = torch.cuda.current_device() if device is None else device
-        self.filter = DepthFilter(self.params, device=self.device, rows=self.rows)
+        if self.layout == "cyclic":
+            self.filter = DepthFilter(self.params, device=self.device, cyclic=(self.block_rows, self.world, self.rank))
+        else:
+            self.filter = DepthFilter(self.params, device=self.device, rows=self.rows)
         dev = torch.device("cuda", self.device)
         self.tdev = dev
         self.ring = [torch.empty((self.H, self.pitch), dtype=torch.uint8, device=dev) for _ in range(n_ring)]
@@ -144,6 +165,26 @@ class ShardedDepthFilter:
         ev.record(self.ctx_stream)
         self._ring_events[b] = ev
 
+    def update_host(self, host_frame, pose: Tuple[tuple, tuple]) -> None:
+        """End-to-end form of update(): `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0 (None
+        elsewhere).  Rank 0 copies it to HBM on the side stream, the frame is broadcast, every rank updates
+        its band; all of it overlapped with the previous frame's kernels."""
+        torch, dist = self.torch, self.dist
+        b = self._k % len(self.ring)
+        self._k += 1
+        buf = self.ring[b]
+        with torch.cuda.stream(self.comm_stream):
+            if self._ring_events[b] is not None:
+                self.comm_stream.wait_event(self._ring_events[b])
+            if self.rank == 0:
+                buf[:, : self.W].copy_(host_frame, non_blocking=True)
+            if self.world > 1:
+                dist.broadcast(buf, src=0, group=self.group)
+        self._launch(buf, pose, True)
+        ev = torch.cuda.Event()
+        ev.record(self.ctx_stream)
+        self._ring_events[b] = ev
+
     # -- results ---------------------------------------------------------------------------
     def gather_state(self):
         """Gather the bands on rank 0: returns (depth, cov2) torch tensors (H, W) on rank 0, else None."""
@@ -151,24 +192,32 @@ class ShardedDepthFilter:
         self._sync_filter()
         if self.world == 1:
             return self.depth_t, self.cov2_t
-        r0, r1 = self.rows
-        max_rows = max(band_rows(self.H, self.params.border, self.world, r)[1] - band_rows(self.H, self.params.border, self.world, r)[0]
-                       for r in range(self.world))
+        send_rows = self._rows_of(self.rank)
+        max_rows = max(len(self._rows_of(r)) for r in range(self.world))
         send = torch.zeros((2, max_rows, self.W), dtype=torch.float64, device=self.depth_t.device)
-        send[0, : r1 - r0] = self.depth_t[r0:r1]
-        send[1, : r1 - r0] = self.cov2_t[r0:r1]
+        idx = torch.as_tensor(send_rows, device=self.depth_t.device)
+        send[0, : len(send_rows)] = self.depth_t.index_select(0, idx)
+        send[1, : len(send_rows)] = self.cov2_t.index_select(0, idx)
         if self.rank == 0:
             recv = [torch.empty_like(send) for _ in range(self.world)]
             dist.gather(send, recv, dst=0, group=self.group)
             for r in range(1, self.world):
-                a, b = band_rows(self.H, self.params.border, self.world, r)
-                self.depth_t[a:b] = recv[r][0, : b - a]
-                self.cov2_t[a:b] = recv[r][1, : b - a]
+                rr = self._rows_of(r)
+                ridx = torch.as_tensor(rr, device=self.depth_t.device)
+                self.depth_t.index_copy_(0, ridx, recv[r][0, : len(rr)])
+                self.cov2_t.index_copy_(0, ridx, recv[r][1, : len(rr)])
             self._sync_current()
             return self.depth_t, self.cov2_t
         dist.gather(send, None, dst=0, group=self.group)
         self._sync_current()
         return None
+
+    def _rows_of(self, r: int) -> np.ndarray:
+        """Rows rank r contributes to the gather (its interior rows; the border rows never change)."""
+        if self.layout == "cyclic":
+            return cyclic_rows(self.H, self.params.border, self.block_rows, self.world, r)
+        a, b = band_rows(self.H, self.params.border, self.world, r)
+        return np.arange(max(a, self.params.border), min(b, self.H - self.params.border), dtype=np.int64)
 
     def _sync_filter(self) -> None:
         self.filter.sync()

@@ -36,6 +36,6 @@ def test_example_driver_runs(tmp_path):
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("*** loop")]
     assert len(lines) == 5
-    n_last = int(re.search(r"cov2 < 2e-2: (\d+)", lines[-1]).group(1))
+    n_last = int(re.search(r"cov2 < 0.5: (\d+)", lines[-1]).group(1))
     mean = float(re.search(r"mean depth ([0-9.]+)", lines[-1]).group(1))
     assert n_last > 50000 and 1.7 < mean < 2.6

@@ -260,6 +260,35 @@ def test_band_contexts_are_bit_identical_to_one_context(DF, seq640):
     assert all(tot[k] == cw[k] for k in tot)
 
 
+def test_cyclic_contexts_are_bit_identical_to_one_context(DF, seq640):
+    """Block-cyclic row ownership (dmf_create_cyclic): three interleaved contexts == one context."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    whole = DF(p)
+    parts = [DF(p, cyclic=(16, 3, r)) for r in range(3)]
+    rows = np.concatenate([f.owned_rows() for f in parts])
+    assert sorted(rows.tolist()) == list(range(p.border, h - p.border))
+    for f in [whole] + parts:
+        f.set_reference(frames[0])
+        f.fill_state(3.0, 3.0)
+    for i in (1, 2, 3):
+        for f in [whole] + parts:
+            f.update(frames[i], seq.T_C_R(i))
+    d, c = whole.download_state()
+    d2, c2 = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    tot = {"active": 0, "ncc_evals": 0, "accepted": 0, "interior": 0}
+    for f in parts:
+        f.download_state(d2, c2)
+        for k in tot:
+            tot[k] += f.counters()[k]
+    cw = whole.counters()
+    for f in [whole] + parts:
+        f.close()
+    assert np.array_equal(d, d2, equal_nan=True) and np.array_equal(c, c2, equal_nan=True)
+    assert all(tot[k] == cw[k] for k in tot)
+
+
 def test_full_size_properties_hd(DF):
     """BASELINE.json config 4 size (1920x1080): determinism (two runs bit-identical), exact parity on a row
     subset against the oracle, work counters consistent."""

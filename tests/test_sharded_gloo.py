@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from slamplay_b200.sharded import band_rows
+from slamplay_b200.sharded import band_rows, cyclic_rows
 
 
 def test_band_rows_tile_the_image_exactly():
@@ -25,13 +25,20 @@ def test_band_rows_tile_the_image_exactly():
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == h - 2 * b
 
 
+def test_cyclic_rows_partition_the_interior():
+    for h, b, blk in [(480, 20, 32), (2160, 20, 32), (376, 20, 7)]:
+        for world in (2, 3, 8):
+            allr = np.concatenate([cyclic_rows(h, b, blk, world, r) for r in range(world)])
+            assert sorted(allr.tolist()) == list(range(b, h - b))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, layout):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
@@ -58,8 +65,13 @@ def _worker(rank, world, port, out_path):
 
         def _launch(self, buf, pose, after_comm):
             cur = np.ascontiguousarray(buf.numpy()[:, : self.W])
-            oracle.update(self.params, self.ref, cur, pose[0], pose[1], self.depth_t.numpy(), self.cov2_t.numpy(),
-                          rows=self.rows, counters=self.cnt)
+            rows = self._rows_of(self.rank)
+            # contiguous runs of owned rows (one per cyclic block, or the whole band)
+            cuts = np.flatnonzero(np.diff(rows) != 1) + 1
+            for run in np.split(rows, cuts):
+                oracle.update(self.params, self.ref, cur, pose[0], pose[1], self.depth_t.numpy(), self.cov2_t.numpy(),
+                              rows=(int(run[0]), int(run[-1]) + 1), counters=self.cnt)
+            self.cnt.frames -= len(cuts)  # one update() per frame, whatever the number of runs
 
         def _sync_filter(self):
             pass
@@ -75,7 +87,7 @@ def _worker(rank, world, port, out_path):
         frames = torch.zeros((seq.n_frames, h, pitch), dtype=torch.uint8)
         for i in range(seq.n_frames):
             frames[i, :, :w] = torch.from_numpy(seq.render_host(i))
-    sf = OracleBand(seq.params)
+    sf = OracleBand(seq.params, layout=layout, block_rows=8)
     assert sf.rows == band_rows(h, seq.params.border, world, rank)
     sf.set_reference(frames[0] if rank == 0 else None)
     sf.fill_state(3.0, 3.0)
@@ -103,7 +115,8 @@ def _worker(rank, world, port, out_path):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_protocol_world2_gloo(tmp_path):
+@pytest.mark.parametrize("layout", ["cyclic", "bands"])
+def test_sharded_protocol_world2_gloo(tmp_path, layout):
     out = tmp_path / "result.txt"
-    mp.spawn(_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(out), layout), nprocs=2, join=True)
     assert out.read_text() == "1 1", "sharded (2 bands) and unsharded results / counters differ"
