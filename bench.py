@@ -267,7 +267,7 @@ def ours(args) -> dict | None:
         frames, pitch = None, (w + 15) // 16 * 16
     poses_all = [seq.T_C_R(i) for i in range(F)]
 
-    sf = ShardedDepthFilter(p, device=local_rank)
+    sf = ShardedDepthFilter(p, device=local_rank, layout=args.layout, block_rows=args.block_rows)
     sf.set_reference(frames[0] if rank == 0 else None)
     ctx_stream = sf.ctx_stream
 
@@ -319,7 +319,7 @@ def ours(args) -> dict | None:
     sf.counters(reset=True)
     per_rank = None
     if world > 1:
-        mine = torch.tensor([ktime["moments_ms"], ktime["setup_ms"], ktime["ncc_ms"], ktime["fuse_ms"], t_enqueue * 1e3],
+        mine = torch.tensor([ktime["setup_ms"], ktime["moments_ms"], ktime["ncc_ms"], ktime["fuse_ms"], t_enqueue * 1e3],
                             dtype=torch.float64, device=device)
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
@@ -348,7 +348,7 @@ def ours(args) -> dict | None:
             "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "frames": F, "updates_per_step": n_upd,
                        "interior_px_per_frame": interior_per_frame, "init_depth": 3.0, "init_cov2": 3.0,
-                       "ncc_window": "7x7", "parallelism": f"row-bands x{world}" if world > 1 else "single GPU",
+                       "ncc_window": "7x7", "parallelism": (f"{args.layout} row blocks x{world}" + (f" ({args.block_rows} rows)" if args.layout == "cyclic" else "")) if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2 ({F * h * pitch / 1e6:.0f} MB of frames per step)",
                        "ncc_evals_per_step": ncc, "active_px_per_step": act, "accepted_per_step": acc},
             "ncc_evals_per_s": ncc / (ms_step * 1e-3),
@@ -364,7 +364,7 @@ def ours(args) -> dict | None:
                               "integer moments (IDP.4A + a per-frame moment table) and is bound by L1/TEX gathers, see profiles/",
                 "kernel_share_of_step": ktime["ncc_ms"] / k_total if k_total else None,
                 "kernel_ms_per_step": {k: ktime[k] for k in ("moments_ms", "setup_ms", "ncc_ms", "fuse_ms")},
-                "per_rank_ms[moments,setup,ncc,fuse,host_step]": per_rank,
+                "per_rank_ms[setup,moments,ncc,fuse,host_step]": per_rank,
                 "whole_step": {"achieved": flops_step / (ms_step * 1e-3) / 1e12 / world,
                                "frac": flops_step / (ms_step * 1e-3) / 1e12 / world / FP32_PEAK_TFLOPS_NOMINAL,
                                "flop_model": "600/NCC + 150/active px + 300/accepted px, per GPU"},
@@ -520,6 +520,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--frames", type=int, default=None, help="override the number of frames (incl. the reference frame)")
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU-baseline sample (default: host cores)")
+    ap.add_argument("--layout", default="cyclic", choices=["cyclic", "bands"], help="row ownership for N > 1")
+    ap.add_argument("--block-rows", type=int, default=8, help="rows per block of the cyclic layout")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-port", action="store_true", help="--impl reference: use the oracle port even at 640x480")

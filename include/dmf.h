@@ -99,8 +99,8 @@ int dmf_default_params(dmf_params *p, int width, int height, int inverse_depth);
 int dmf_create(const dmf_params *params, int device, int row_begin, int row_end, dmf_ctx **out);
 /*
  * Block-cyclic row ownership for multi-GPU runs (SURVEY.md 8e "fallback if contiguous bands do not
- * balance"): the interior rows are cut into blocks of `block_rows` rows, dealt round-robin to `n_parts`
- * contexts; this context is number `part`.  Convergence varies smoothly down the image, so interleaved
+ * balance"): the interior rows are cut into blocks of `block_rows` rows, dealt to `n_parts`
+ * contexts in boustrophedon order (0..n-1, n-1..0, ...); this context is number `part`.  Convergence varies smoothly down the image, so interleaved
  * blocks give every GPU the same mix of short and long epipolar searches.  Upload / download move the
  * owned rows only.  dmf_get_rows lists the owned image rows in local order (rows_out may be NULL to
  * query the count).
@@ -154,7 +154,7 @@ int dmf_sync(dmf_ctx *ctx);
 
 /*
  * Optional per-kernel timing for the roofline report (bench.py): with timing enabled every update()
- * brackets its four kernels (block moments, setup, ncc, fuse) with CUDA events on the context stream.
+ * brackets its four kernels (in launch order: setup, block moments, ncc, fuse) with CUDA events on the context stream.
  * dmf_get_timing synchronises and returns the accumulated milliseconds per kernel class and the number
  * of frames they cover.  Off by default (the events cost ~1 % on small frames).
  */

@@ -132,7 +132,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     const int rows = c->n_rows;
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
-        dim3 mgrid((p.width - 7 + 31) / 32, (p.height - 7 + 7) / 8);
+        dim3 mgrid((p.width - 15 + dmf::MOM_THREADS - 1) / dmf::MOM_THREADS, (p.height - 8 + dmf::MOM_STRIP - 1) / dmf::MOM_STRIP);
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         if (c->timing_on) {
             for (int i = 0; i < 5; ++i) {
@@ -147,7 +147,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         }
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
-        dmf::moments_kernel<<<mgrid, 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_row_need);
+        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_row_need);
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
@@ -230,8 +230,13 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             if (row_end > row_begin) c->io_spans.push_back({row_begin, row_end});
         } else {             // block-cyclic: blocks of block_rows interior rows dealt round-robin
             c->row0 = lo; c->blk = block_rows; c->cyc = n_parts; c->ph = part; c->n_rows = 0;
-            for (int b = part; lo + b * block_rows < hi; b += n_parts) {
-                const int y0 = lo + b * block_rows, y1 = (y0 + block_rows < hi) ? y0 + block_rows : hi;
+            // round k deals blocks k*n_parts .. k*n_parts + n_parts-1; odd rounds in reverse order (boustrophedon).
+            // Only the last block of the image can be short, and a context's rounds stop at its first missing block.
+            for (int k = 0;; ++k) {
+                const int pos = (k & 1) ? (n_parts - 1 - part) : part;
+                const int y0 = lo + (k * n_parts + pos) * block_rows;
+                if (y0 >= hi) break;
+                const int y1 = (y0 + block_rows < hi) ? y0 + block_rows : hi;
                 c->spans.push_back({y0, y1});
                 c->n_rows += y1 - y0;
             }

@@ -87,8 +87,9 @@ static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 struct KParams {
     int width, height, border;
     // Rows owned by this context: local row rl in [0, n_rows) is image row
-    //   y = row0 + ((rl / blk) * cyc + ph) * blk + rl % blk
-    // (block-cyclic: blocks of `blk` rows dealt round-robin to `cyc` contexts, this one being `ph`;
+    //   y = row0 + ((rl / blk) * cyc + pos) * blk + rl % blk,   pos = ph (even rl / blk) or cyc-1-ph (odd)
+    // (block-cyclic: blocks of `blk` rows dealt to `cyc` contexts in boustrophedon order, so a load that
+    //  varies linearly down the image splits evenly; this context is number `ph`;
     //  a contiguous band is blk = n_rows, cyc = 1, ph = 0).
     int row0, blk, cyc, ph, n_rows;
     int wi;                  // width - 2*border
@@ -151,7 +152,8 @@ __device__ __forceinline__ double int2double_fast(int k) {
 }
 __device__ __forceinline__ int row_of(const KParams &P, int rl) {
     const int b = rl / P.blk;
-    return P.row0 + (b * P.cyc + P.ph) * P.blk + (rl - b * P.blk);
+    const int pos = (b & 1) ? (P.cyc - 1 - P.ph) : P.ph;
+    return P.row0 + (b * P.cyc + pos) * P.blk + (rl - b * P.blk);
 }
 // sample position parameter of iteration k of the loop ref:432, l_k = -half + step*k
 __device__ __forceinline__ double sample_l(double half, double step, int k) {
@@ -336,83 +338,97 @@ __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint3
 
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
-// Integer moments of the 8x8 u8 block whose rows are (lo[j], hi[j]) = bytes 0..3 / 4..7.
-// Window (a,b) = columns a..a+6, rows b..b+6 of the block.
-struct BlockMoments {
-    int S00, S10, S01, S11;                                                   // window sums
-    int G0000, G1010, G0101, G1111, G0010, G0111, G0001, G1011, G0011, G1001;  // Gram sums
-};
-__device__ __forceinline__ BlockMoments block_moments(const uint32_t (&lo)[8], const uint32_t (&hi)[8]) {
-    const uint32_t ONES = 0x01010101u;
-    int s0t = 0, s0m = 0, s0b = 0, s1t = 0, s1m = 0, s1b = 0;
-    int q0t = 0, q0m = 0, q0b = 0, q1t = 0, q1m = 0, q1b = 0;
-    int ht = 0, hm = 0, hb = 0;
-    int v0 = 0, v1 = 0, d01 = 0, d10 = 0;
-    uint32_t p0l = 0, p0h = 0, p1l = 0, p1h = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t x0l = lo[j], x0h = hi[j] & 0x00FFFFFFu;                    // columns 0..6
-        const uint32_t x1l = __funnelshift_r(lo[j], hi[j], 8), x1h = hi[j] >> 8;  // columns 1..7
-        if (j == 0) {
-            s0t = dp4(x0l, ONES, dp4(x0h, ONES, 0)); s1t = dp4(x1l, ONES, dp4(x1h, ONES, 0));
-            q0t = dp4(x0l, x0l, dp4(x0h, x0h, 0));   q1t = dp4(x1l, x1l, dp4(x1h, x1h, 0));
-            ht = dp4(x0l, x1l, dp4(x0h, x1h, 0));
-        } else if (j == 7) {
-            s0b = dp4(x0l, ONES, dp4(x0h, ONES, 0)); s1b = dp4(x1l, ONES, dp4(x1h, ONES, 0));
-            q0b = dp4(x0l, x0l, dp4(x0h, x0h, 0));   q1b = dp4(x1l, x1l, dp4(x1h, x1h, 0));
-            hb = dp4(x0l, x1l, dp4(x0h, x1h, 0));
-        } else {
-            s0m = dp4(x0l, ONES, dp4(x0h, ONES, s0m)); s1m = dp4(x1l, ONES, dp4(x1h, ONES, s1m));
-            q0m = dp4(x0l, x0l, dp4(x0h, x0h, q0m));   q1m = dp4(x1l, x1l, dp4(x1h, x1h, q1m));
-            hm = dp4(x0l, x1l, dp4(x0h, x1h, hm));
-        }
-        if (j > 0) {
-            v0 = dp4(p0l, x0l, dp4(p0h, x0h, v0));
-            v1 = dp4(p1l, x1l, dp4(p1h, x1h, v1));
-            d01 = dp4(p0l, x1l, dp4(p0h, x1h, d01));
-            d10 = dp4(p1l, x0l, dp4(p1h, x0h, d10));
-        }
-        p0l = x0l; p0h = x0h; p1l = x1l; p1h = x1h;
-    }
-    BlockMoments m;
-    m.S00 = s0t + s0m; m.S01 = s0m + s0b; m.S10 = s1t + s1m; m.S11 = s1m + s1b;
-    m.G0000 = q0t + q0m; m.G0101 = q0m + q0b; m.G1010 = q1t + q1m; m.G1111 = q1m + q1b;
-    m.G0010 = ht + hm; m.G0111 = hm + hb;
-    m.G0001 = v0; m.G1011 = v1; m.G0011 = d01; m.G1001 = d10;
-    return m;
-}
-
 // K2m: once per current frame — the frame-only part of every possible NCC: window sum and centred
 // Gram sums of the 8x8 block at each position (x,y) = top-left tap.  A sample whose top-left tap is
 // (bx,by) needs   mom1 at (bx,by),(bx+1,by),(bx,by+1),(bx+1,by+1)  and  mom2 at (bx,by):
 //   mom1(x,y) = { S(x,y), 49*Q - S^2, 49*H - S(x,y)S(x+1,y), 49*V - S(x,y)S(x,y+1) }   (Q,H,V: squares,
 //   mom2(x,y) = { 49*D1 - S(x,y)S(x+1,y+1), 49*D2 - S(x+1,y)S(x,y+1) }                  horizontal / vertical /
 //                                                                                        diagonal neighbour products)
-__global__ void __launch_bounds__(256) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
+// A thread owns one column x and slides the 7-row window down a strip of MOM_STRIP rows: per step the
+// row (pair) leaving the window is subtracted and the row (pair) entering it is added, 28 IDP.4A per
+// position instead of 176 for a from-scratch 7x7 evaluation.  Adjacent threads hold adjacent columns,
+// so the row loads and the 24-byte table stores are coalesced.
+#ifndef DMF_MOM_STRIP
+#define DMF_MOM_STRIP 16
+#endif
+#ifndef DMF_MOM_THREADS
+#define DMF_MOM_THREADS 128
+#endif
+constexpr int MOM_STRIP = DMF_MOM_STRIP;
+constexpr int MOM_THREADS = DMF_MOM_THREADS;
+
+struct RowBytes { uint32_t x0l, x0h, x1l, x1h; };  // columns 0..6 (x0) and 1..7 (x1) of one block row
+__device__ __forceinline__ RowBytes load_row_bytes(const uint32_t *wp, unsigned sh) {
+    uint32_t lo, hi;
+    load_row8(wp, sh, lo, hi);
+    return {lo, hi & 0x00FFFFFFu, __funnelshift_r(lo, hi, 8), hi >> 8};
+}
+struct RowSums { int s0, s1, q, h; };  // one row: sum cols 0..6, sum cols 1..7, sum of squares cols 0..6, neighbour products
+__device__ __forceinline__ RowSums row_sums(const RowBytes &r) {
+    const uint32_t ONES = 0x01010101u;
+    return {dp4(r.x0l, ONES, dp4(r.x0h, ONES, 0)), dp4(r.x1l, ONES, dp4(r.x1h, ONES, 0)),
+            dp4(r.x0l, r.x0l, dp4(r.x0h, r.x0h, 0)), dp4(r.x0l, r.x1l, dp4(r.x0h, r.x1h, 0))};
+}
+struct PairSums { int v, d1, d2; };  // rows (a, a+1): vertical and the two diagonal neighbour products
+__device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes &b) {
+    return {dp4(a.x0l, b.x0l, dp4(a.x0h, b.x0h, 0)), dp4(a.x0l, b.x1l, dp4(a.x0h, b.x1h, 0)),
+            dp4(a.x1l, b.x0l, dp4(a.x1h, b.x0h, 0))};
+}
+
+__global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                       int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch,
                                                       const uint8_t *__restrict__ row_need) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x > width - 8 || y > height - 8) return;
-    if (!row_need[blockIdx.y]) return;  // no sample of this frame reads these 8 table rows (CTA-uniform)
-    const uint8_t *base = img + (size_t)y * pitch + x;
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - mis);
+    const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
+    const int y0 = blockIdx.y * MOM_STRIP;
+    const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
+    // skip strips none of whose 8-row groups is read by a sample of this frame (CTA-uniform)
+    bool need = false;
+    for (int g = y0 >> 3; g <= (min(y0 + MOM_STRIP, height) - 1) >> 3; ++g) need |= (row_need[g] != 0);
+    if (!need || x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
+
+    const uint8_t *base = img + (size_t)y0 * pitch + x;
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - (sh >> 3));
     const int pw = pitch >> 2;
-    uint32_t lo[8], hi[8];
+
+    // window state for position y0: single-row sums over rows y0..y0+6, pair sums over (y0,y0+1)..(y0+6,y0+7)
+    int S0 = 0, S1 = 0, Q = 0, H = 0, V = 0, D1 = 0, D2 = 0;
+    RowBytes prev = load_row_bytes(wp, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) load_row8(wp + j * pw, mis * 8u, lo[j], hi[j]);
-    const BlockMoments m = block_moments(lo, hi);
-    int4 a;
-    a.x = m.S00;
-    a.y = NCC_AREA * m.G0000 - m.S00 * m.S00;
-    a.z = NCC_AREA * m.G0010 - m.S00 * m.S10;
-    a.w = NCC_AREA * m.G0001 - m.S00 * m.S01;
-    int2 b;
-    b.x = NCC_AREA * m.G0011 - m.S00 * m.S11;
-    b.y = NCC_AREA * m.G1001 - m.S10 * m.S01;
-    mom1[(size_t)y * mom_pitch + x] = a;
-    mom2[(size_t)y * mom_pitch + x] = b;
+    for (int j = 0; j < 7; ++j) {
+        const RowBytes next = load_row_bytes(wp + (j + 1) * pw, sh);
+        const RowSums r = row_sums(prev);
+        const PairSums p = pair_sums(prev, next);
+        S0 += r.s0; S1 += r.s1; Q += r.q; H += r.h; V += p.v; D1 += p.d1; D2 += p.d2;
+        prev = next;
+    }
+    // sliding: rows leaving (old_a = y, old_b = y+1) and entering (new_a = y+7, new_b = y+8)
+    RowBytes old_a = load_row_bytes(wp, sh), old_b = load_row_bytes(wp + pw, sh);
+    RowBytes new_a = prev;  // row y0+7
+    RowBytes new_b = load_row_bytes(wp + 8 * pw, sh);
+    for (int y = y0; y < y_end; ++y) {
+        const RowSums ro = row_sums(old_a), rn = row_sums(new_a);
+        const PairSums po = pair_sums(old_a, old_b), pn = pair_sums(new_a, new_b);
+        const int S0n = S0 - ro.s0 + rn.s0, S1n = S1 - ro.s1 + rn.s1;  // window sums of position y+1: S01, S11 of y
+        int4 a;
+        a.x = S0;
+        a.y = NCC_AREA * Q - S0 * S0;
+        a.z = NCC_AREA * H - S0 * S1;
+        a.w = NCC_AREA * V - S0 * S0n;
+        int2 b;
+        b.x = NCC_AREA * D1 - S0 * S1n;
+        b.y = NCC_AREA * D2 - S1 * S0n;
+        mom1[(size_t)y * mom_pitch + x] = a;
+        mom2[(size_t)y * mom_pitch + x] = b;
+        // advance the window to position y+1
+        S0 = S0n; S1 = S1n;
+        Q += rn.q - ro.q; H += rn.h - ro.h;
+        V += pn.v - po.v; D1 += pn.d1 - po.d1; D2 += pn.d2 - po.d2;
+        old_a = old_b; new_a = new_b;
+        const int yn = y + 1;
+        old_b = load_row_bytes(wp + (size_t)(yn + 1 - y0) * pw, sh);
+        new_b = load_row_bytes(wp + (size_t)(min(yn + 8, height - 1) - y0) * pw, sh);
+    }
 }
 
 // One NCC (ref:449-480) of the reference patch against the current image at the sub-pixel position

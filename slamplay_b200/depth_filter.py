@@ -180,7 +180,7 @@ class DepthFilter:
         ms = (C.c_double * 4)()
         n = C.c_uint64()
         self._ck(self._lib.dmf_get_timing(self._ctx, ms, C.byref(n), int(reset)), "dmf_get_timing")
-        return {"moments_ms": ms[0], "setup_ms": ms[1], "ncc_ms": ms[2], "fuse_ms": ms[3], "frames": int(n.value)}
+        return {"setup_ms": ms[0], "moments_ms": ms[1], "ncc_ms": ms[2], "fuse_ms": ms[3], "frames": int(n.value)}  # launch order
 
     def enable_flags(self, on: bool = True) -> None:
         self._ck(self._lib.dmf_enable_flags(self._ctx, int(on)), "dmf_enable_flags")

@@ -40,11 +40,14 @@ def cyclic_rows(height: int, border: int, block_rows: int, world: int, rank: int
     """Interior rows of `rank` under block-cyclic ownership (same rule as dmf_create_cyclic)."""
     lo, hi = border, height - border
     rows = []
-    b = rank
-    while lo + b * block_rows < hi:
-        y0 = lo + b * block_rows
+    k = 0
+    while True:  # round k deals blocks k*world .. k*world + world-1, odd rounds in reverse (boustrophedon)
+        pos = (world - 1 - rank) if (k & 1) else rank
+        y0 = lo + (k * world + pos) * block_rows
+        if y0 >= hi:
+            break
         rows.extend(range(y0, min(y0 + block_rows, hi)))
-        b += world
+        k += 1
     return np.array(rows, dtype=np.int64)
 
 
@@ -60,7 +63,7 @@ class ShardedDepthFilter:
     """Depth filter whose state is split into row bands over the ranks of a process group."""
 
     def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 3,
-                 layout: str = "cyclic", block_rows: int = 32):
+                 layout: str = "cyclic", block_rows: int = 8):
         """layout "cyclic" (default): blocks of `block_rows` interior rows dealt round-robin to the ranks —
         convergence varies smoothly down the image, so this balances the per-rank work; "bands": one
         contiguous band per rank (SURVEY.md 8e first choice; measured 4x imbalance on the 4K sequence)."""
