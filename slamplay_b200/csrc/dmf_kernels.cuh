@@ -431,15 +431,21 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
     }
 }
 
-// One NCC (ref:449-480) of the reference patch against the current image at the sub-pixel position
-// with integer part (ix,iy) and bilinear fractions (fx,fy) (ref:167-168).
+// The integer part of one NCC (ref:449-480): everything that depends on the integer position (ix,iy) of
+// the sample but not on its bilinear fractions — the four centred cross sums with the reference patch and
+// the ten centred Gram sums of the block.  Consecutive samples of a search are 0.7 px apart, so about one
+// in three (axis-aligned lines) falls on the same integer position as its predecessor and reuses these
+// 14 integers without touching memory.
 // R0lo/R0hi: reference rows as bytes (r0..r3),(r4,r5,r6,0) — they meet block columns 0..6 (window a=0);
 // R1lo/R1hi: the same rows shifted by one byte, (0,r0,r1,r2),(r3..r6) — they meet block columns 1..7
 // (window a=1) of the SAME unshifted block words, so the block needs no per-sample byte shifts.
-// nSr = -sum r, den1 = 49*sum r^2 - (sum r)^2.
-__device__ __forceinline__ double ncc_at(const KParams &P, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
-                                         const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr, double den1,
-                                         int ix, int iy, double fx, double fy) {
+struct SampleInts {
+    int cR00, cR10, cR01, cR11;                                                // 49*R - Sr*S per window
+    int g0000, g1010, g0101, g1111, g0010, g0111, g0001, g1011, g0011, g1001;  // 49*G - S*S'
+};
+__device__ __forceinline__ SampleInts gather_ints(const KParams &P, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
+                                                  const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr, int ix,
+                                                  int iy) {
     const unsigned off = (unsigned)(iy - 3) * (unsigned)P.curr_pitch + (unsigned)(ix - 3);
     const unsigned sh = (off & 3u) * 8u;
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.curr + (size_t)(off & ~3u));
@@ -465,23 +471,30 @@ __device__ __forceinline__ double ncc_at(const KParams &P, const uint32_t (&R0lo
             R10 = dp4(R1lo[j], lo[j], dp4(R1hi[j], hi[j], R10));
         }
     }
+    SampleInts s;
     // exact centring in int32 (all terms < 2^31)
-    const int cR00 = NCC_AREA * R00 + nSr * m00.x, cR10 = NCC_AREA * R10 + nSr * m10.x;
-    const int cR01 = NCC_AREA * R01 + nSr * m01.x, cR11 = NCC_AREA * R11 + nSr * m11.x;
+    s.cR00 = NCC_AREA * R00 + nSr * m00.x; s.cR10 = NCC_AREA * R10 + nSr * m10.x;
+    s.cR01 = NCC_AREA * R01 + nSr * m01.x; s.cR11 = NCC_AREA * R11 + nSr * m11.x;
+    s.g0000 = m00.y; s.g1010 = m10.y; s.g0101 = m01.y; s.g1111 = m11.y;
+    s.g0010 = m00.z; s.g0111 = m01.z; s.g0001 = m00.w; s.g1011 = m10.w;
+    s.g0011 = md.x; s.g1001 = md.y;
+    return s;
+}
 
-    // FP64 combination with the bilinear weights of ref:169-172
+// The FP64 part: combination with the bilinear weights of ref:169-172 (fractions fx, fy, ref:167-168);
+// den1 = 49*sum r^2 - (sum r)^2.  int -> double conversions run on the XU pipe (I2F.F64), idle otherwise.
+__device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, double fx, double fy) {
     const double gx = 1.0 - fx, gy = 1.0 - fy;
     const double w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
-    // int -> double conversions run on the XU pipe (I2F.F64), idle otherwise
-    double num = w00 * (double)cR00;
-    num = fma(w10, (double)cR10, num);
-    num = fma(w01, (double)cR01, num);
-    num = fma(w11, (double)cR11, num);
+    double num = w00 * (double)s.cR00;
+    num = fma(w10, (double)s.cR10, num);
+    num = fma(w01, (double)s.cR01, num);
+    num = fma(w11, (double)s.cR11, num);
     // den2 = w^T G w  with G the centred Gram matrix over the windows (00,10,01,11)
-    const double g0000 = (double)m00.y, g1010 = (double)m10.y, g0101 = (double)m01.y, g1111 = (double)m11.y;
-    const double g0010 = (double)m00.z, g0111 = (double)m01.z;
-    const double g0001 = (double)m00.w, g1011 = (double)m10.w;
-    const double g0011 = (double)md.x, g1001 = (double)md.y;
+    const double g0000 = (double)s.g0000, g1010 = (double)s.g1010, g0101 = (double)s.g0101, g1111 = (double)s.g1111;
+    const double g0010 = (double)s.g0010, g0111 = (double)s.g0111;
+    const double g0001 = (double)s.g0001, g1011 = (double)s.g1011;
+    const double g0011 = (double)s.g0011, g1001 = (double)s.g1001;
     double a0 = w00 * g0000; a0 = fma(w10, g0010, a0); a0 = fma(w01, g0001, a0); a0 = fma(w11, g0011, a0);
     double a1 = w00 * g0010; a1 = fma(w10, g1010, a1); a1 = fma(w01, g1001, a1); a1 = fma(w11, g1011, a1);
     double a2 = w00 * g0001; a2 = fma(w10, g1001, a2); a2 = fma(w01, g0101, a2); a2 = fma(w11, g0111, a2);
@@ -566,6 +579,8 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
 
             double best_v = -1.0;  // ref:430
             int best_k = -1;
+            int pix = -1, piy = -1;  // integer position whose SampleInts are held
+            SampleInts si{};
             // position of the first sample; inside the loop the position of sample j+1 is computed
             // before the NCC of sample j so its FP64 -> int chain is off the critical path
             double sx, sy;
@@ -586,7 +601,11 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 const bool ok = cx >= P.border && cy >= P.border && cx + P.border < P.width && cy + P.border <= P.height;
                 if (!ok) continue;
                 const int ix = (int)cx, iy = (int)cy;  // positive: trunc == floor
-                const double v = ncc_at(P, R0lo, R0hi, R1lo, R1hi, nSr, den1, ix, iy, cx - (double)ix, cy - (double)iy);
+                if (ix != pix || iy != piy) {
+                    si = gather_ints(P, R0lo, R0hi, R1lo, R1hi, nSr, ix, iy);
+                    pix = ix; piy = iy;
+                }
+                const double v = ncc_combine(si, den1, cx - (double)ix, cy - (double)iy);
                 ++my_evals;
                 if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
