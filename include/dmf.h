@@ -201,6 +201,17 @@ int dmf_set_truth(dmf_ctx *ctx, const double *truth_host, size_t step);
 int dmf_evaluate_depth(dmf_ctx *ctx, double max_variance, double *sum_sq, uint64_t *count);
 int dmf_variance_mask(dmf_ctx *ctx, double max_variance, uint8_t *mask_host, size_t step);
 
+/*
+ * getPointCloudFromImageAndDistance (utils/pointcloud/pointcloud_from_image_depth.h:42-89) as called at
+ * ref:296-300: mask = getMaskFromVariance(depth_cov2, max_variance), distance = depth, T = identity.
+ * `color_host`: the reference colour image (`channels` = 3 BGR as cv::imread gives it, or 1 / 4), full image.
+ * Writes up to `capacity` points in the reference's scan order: xyz as 3 floats (PointXYZRGB narrows to
+ * float), rgb as 3 bytes (r,g,b).  *n_points receives the number of valid points (may exceed capacity).
+ * Contiguous-band contexts only.
+ */
+int dmf_point_cloud(dmf_ctx *ctx, const uint8_t *color_host, size_t color_step, int channels, double max_variance,
+                    float *xyz_host, uint8_t *rgb_host, uint64_t capacity, uint64_t *n_points);
+
 #ifdef __cplusplus
 }
 #endif

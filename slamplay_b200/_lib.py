@@ -83,6 +83,7 @@ DMF_SYMBOLS = {
     "dmf_set_truth": (C.c_int, [_vp, _vp, C.c_size_t]),
     "dmf_evaluate_depth": (C.c_int, [_vp, C.c_double, _P(C.c_double), _P(C.c_uint64)]),
     "dmf_variance_mask": (C.c_int, [_vp, C.c_double, _vp, C.c_size_t]),
+    "dmf_point_cloud": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_double, _vp, _vp, C.c_uint64, _P(C.c_uint64)]),
 }
 SYNTH_DEVICE_SYMBOLS = {
     "dmf_synth_render_device": (C.c_int, [_P(SynthScene), _P(SynthCamera), _vp, C.c_size_t, _vp, C.c_size_t, _vp]),

@@ -636,4 +636,55 @@ int dmf_variance_mask(dmf_ctx *c, double max_variance, uint8_t *mask_host, size_
     return DMF_OK;
 }
 
+int dmf_point_cloud(dmf_ctx *c, const uint8_t *color_host, size_t color_step, int channels, double max_variance,
+                    float *xyz_host, uint8_t *rgb_host, uint64_t capacity, uint64_t *n_points) {
+    if (!c || !color_host || !xyz_host || !rgb_host || !n_points) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: NULL argument");
+    if (channels != 1 && channels != 3 && channels != 4) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: channels must be 1, 3 or 4");
+    const dmf_params &p = c->prm;
+    if (color_step < (size_t)p.width * channels) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: step < width*channels");
+    if (c->cyc != 1) return fail(c, DMF_ERR_STATE, "dmf_point_cloud: needs a context that owns a contiguous band");
+    CU(cudaSetDevice(c->device));
+    const int y0 = c->row0, n_rows = c->n_rows;
+    *n_points = 0;
+    if (n_rows <= 0) return DMF_OK;
+    uint8_t *d_color = nullptr, *d_rgb = nullptr;
+    float *d_xyz = nullptr;
+    unsigned int *d_rows = nullptr;
+    const size_t cpitch = (size_t)p.width * channels;
+    const uint64_t max_pts = (uint64_t)n_rows * (uint64_t)(p.width - 2 * p.border);
+    const uint64_t cap = capacity < max_pts ? capacity : max_pts;
+    int rc = DMF_OK;
+    auto cleanup = [&]() { cudaFree(d_color); cudaFree(d_rgb); cudaFree(d_xyz); cudaFree(d_rows); };
+#define CUP(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) { rc = fail(c, DMF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); cleanup(); return rc; } \
+    } while (0)
+    CUP(cudaMalloc(&d_color, cpitch * p.height));
+    CUP(cudaMalloc(&d_rows, (size_t)(n_rows + 1) * sizeof(unsigned int)));
+    CUP(cudaMalloc(&d_xyz, (cap ? cap : 1) * 3 * sizeof(float)));
+    CUP(cudaMalloc(&d_rgb, (cap ? cap : 1) * 3));
+    CUP(cudaMemcpy2DAsync(d_color, cpitch, color_host, color_step, cpitch, p.height, cudaMemcpyHostToDevice, c->stream));
+    dmf::cloud_count_kernel<<<n_rows, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, p.width, p.border, p.width - p.border, y0,
+                                                           max_variance, d_rows);
+    dmf::cloud_scan_kernel<<<1, 1024, 0, c->stream>>>(d_rows, n_rows);
+    dmf::cloud_write_kernel<<<n_rows, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, p.width, d_color, (int)cpitch, channels, p.border,
+                                                           p.width - p.border, y0, max_variance, p.cx, p.cy, p.fx, p.fy, d_rows,
+                                                           d_xyz, d_rgb, cap);
+    CUP(cudaGetLastError());
+    unsigned int total = 0;
+    CUP(cudaMemcpyAsync(&total, d_rows + n_rows, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+    CUP(cudaStreamSynchronize(c->stream));
+    const uint64_t n_out = total < cap ? total : cap;
+    if (n_out) {
+        CUP(cudaMemcpyAsync(xyz_host, d_xyz, n_out * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CUP(cudaMemcpyAsync(rgb_host, d_rgb, n_out * 3, cudaMemcpyDeviceToHost, c->stream));
+        CUP(cudaStreamSynchronize(c->stream));
+    }
+#undef CUP
+    cleanup();
+    *n_points = total;
+    return DMF_OK;
+}
+
 }  // extern "C"

@@ -772,4 +772,103 @@ __global__ void variance_mask_kernel(const double *__restrict__ var, int pitch, 
     mask[(size_t)y * mask_pitch + x] = var[(size_t)y * pitch + x] > max_variance ? 0 : 255;
 }
 
+// ----------------------------------------------------------------------------------------
+// "next" row: getPointCloudFromImageAndDistance, utils/pointcloud/pointcloud_from_image_depth.h:42-89,
+// as called at ref:296-300: mask = variance > max_variance ? 0 : 255 (getMaskFromVariance ref:199-204), distance =
+// the depth map (|OP| along the ray), T = identity.  Points come out in the reference's scan order (rows, then
+// columns): pass 1 counts the valid pixels of every interior row, a one-block scan turns counts into offsets,
+// pass 2 writes each row's points at its offset in column order.
+__device__ __forceinline__ bool cloud_valid(double dist, double var, double max_variance) {
+    return !(dist == 0) && !(var > max_variance);  // `distance == 0 || valid == 0 -> continue` (:66-67)
+}
+
+__global__ void __launch_bounds__(256) cloud_count_kernel(const double *__restrict__ dist, const double *__restrict__ var, int pitch,
+                                                          int x0, int x1, int y0, double max_variance,
+                                                          unsigned int *__restrict__ row_count) {
+    const int y = y0 + blockIdx.x;
+    unsigned n = 0;
+    for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x)
+        n += cloud_valid(dist[(size_t)y * pitch + x], var[(size_t)y * pitch + x], max_variance) ? 1u : 0u;
+    __shared__ unsigned s[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        row_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of n_rows counts in place (single block); total -> row_count[n_rows]
+__global__ void __launch_bounds__(1024) cloud_scan_kernel(unsigned int *row_count, int n_rows) {
+    __shared__ unsigned s[1024];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_rows; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < n_rows ? row_count[i] : 0u;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n_rows) row_count[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += s[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_count[n_rows] = carry;
+}
+
+__global__ void __launch_bounds__(256) cloud_write_kernel(const double *__restrict__ dist, const double *__restrict__ var, int pitch,
+                                                          const uint8_t *__restrict__ color, int color_pitch, int channels,
+                                                          int x0, int x1, int y0, double max_variance, double cx, double cy,
+                                                          double fx, double fy, const unsigned int *__restrict__ row_offset,
+                                                          float *__restrict__ xyz, uint8_t *__restrict__ rgb,
+                                                          unsigned long long capacity) {
+    const int y = y0 + blockIdx.x;
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_run;
+    if (threadIdx.x == 0) s_run = row_offset[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int xb = x0; xb < x1; xb += blockDim.x) {
+        const int x = xb + threadIdx.x;
+        bool ok = false;
+        double d = 0;
+        if (x < x1) {
+            d = dist[(size_t)y * pitch + x];
+            ok = cloud_valid(d, var[(size_t)y * pitch + x], max_variance);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) { before += w < warp ? s_warp[w] : 0u; total += s_warp[w]; }
+        if (ok) {
+            const unsigned long long slot = (unsigned long long)s_run + before + __popc(bal & ((1u << lane) - 1u));
+            if (slot < capacity) {
+                // point = normalize((u-cx)/fx, (v-cy)/fy, 1) * distance   (:68-73), stored as float like PointXYZRGB
+                double px = ((double)x - cx) / fx, py = ((double)y - cy) / fy, pz = 1.0;
+                const double z = px * px + (py * py + pz * pz);
+                if (z > 0) { const double nrm = sqrt(z); px /= nrm; py /= nrm; pz /= nrm; }
+                xyz[3 * slot + 0] = (float)(px * d); xyz[3 * slot + 1] = (float)(py * d); xyz[3 * slot + 2] = (float)(pz * d);
+                const uint8_t *c = color + (size_t)y * color_pitch + (size_t)x * channels;
+                rgb[3 * slot + 0] = channels >= 3 ? c[2] : c[0];  // r (:79-81: b,g,r = data[0..2])
+                rgb[3 * slot + 1] = channels >= 3 ? c[1] : c[0];
+                rgb[3 * slot + 2] = c[0];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += total;
+        __syncthreads();
+    }
+}
+
 }  // namespace dmf

@@ -246,6 +246,25 @@ class DepthFilter:
         return m
 
 
+    def point_cloud(self, color: np.ndarray, max_variance: Optional[float] = None):
+        """getPointCloudFromImageAndDistance (utils/pointcloud/pointcloud_from_image_depth.h:42-89) as called at
+        ref:296-300.  color: (H, W, 3) BGR or (H, W) gray uint8.  Returns (xyz float32 (N,3), rgb uint8 (N,3))."""
+        if max_variance is None:
+            max_variance = 2.0 * self.params.min_cov
+        p = self.params
+        if color.dtype != np.uint8 or color.shape[:2] != (p.height, p.width):
+            raise ValueError("color must be a uint8 image of the filter's size")
+        channels = 1 if color.ndim == 2 else color.shape[2]
+        color = np.ascontiguousarray(color)
+        cap = (p.height - 2 * p.border) * (p.width - 2 * p.border)
+        xyz = np.zeros((cap, 3), np.float32)
+        rgb = np.zeros((cap, 3), np.uint8)
+        n = C.c_uint64()
+        self._ck(self._lib.dmf_point_cloud(self._ctx, color.ctypes.data, color.strides[0], channels, float(max_variance),
+                                           xyz.ctypes.data, rgb.ctypes.data, cap, C.byref(n)), "dmf_point_cloud")
+        return xyz[: n.value], rgb[: n.value]
+
+
 # ---------------------------------------------------------------------------------------------
 # Strict drop-in: the reference's free function.
 _strict_ctx: dict = {}

@@ -365,6 +365,34 @@ def test_evaluate_depth_and_variance_mask(DF, seq640):
     assert np.array_equal(mask, m_ref)
 
 
+def test_point_cloud_export(DF, seq640):
+    """'next' row: getPointCloudFromImageAndDistance (utils/pointcloud/pointcloud_from_image_depth.h:42-89)."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    for i in range(1, 6):
+        f.update(frames[i], seq.T_C_R(i))
+    d, c = f.download_state()
+    thr = float(np.median(c[20:-20, 20:-20]))
+    color = np.stack([frames[0], 255 - frames[0], frames[0] // 2], axis=-1)  # BGR
+    xyz, rgb = f.point_cloud(color, thr)
+    f.close()
+    mask = np.zeros((h, w), np.uint8)
+    oracle.lib().dmo_variance_mask(w, h, c.ctypes.data, c.strides[0], thr, mask.ctypes.data, w)
+    cap = (h - 40) * (w - 40)
+    xo = np.zeros((cap, 3), np.float32)
+    ro = np.zeros((cap, 3), np.uint8)
+    po = oracle.to_params(p)
+    n = oracle.lib().dmo_point_cloud(C.byref(po), color.ctypes.data, color.strides[0], 3, d.ctypes.data, d.strides[0],
+                                     mask.ctypes.data, w, xo.ctypes.data, ro.ctypes.data, cap)
+    assert n == len(xyz) and 0.3 * cap < n < 0.7 * cap
+    assert np.array_equal(rgb, ro[:n])
+    assert np.allclose(xyz, xo[:n], rtol=1e-6, atol=0)  # float32 of the same FP64 values (ulp-level differences)
+
+
 def test_api_errors(DF, seq640):
     from slamplay_b200.depth_filter import DmfError
     seq, frames = seq640
