@@ -46,6 +46,7 @@ struct dmf_ctx_impl {
     dmf::Ctrl *d_ctrl = nullptr;
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
     int2 *d_mom2 = nullptr;
+    uint2 *d_currx = nullptr;                  // expanded current frame (expand_kernel)
     int n_pix = 0, ncc_grid = 0;
     // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
     bool timing_on = false;
@@ -127,7 +128,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.wi = p.width - 2 * p.border;
     K.n_pix = c->n_pix;
     K.rec = c->d_rec;
-    K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width;
+    K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width; K.currx = c->d_currx;
     K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.ctrl = c->d_ctrl;
     const int rows = c->n_rows;
     if (rows > 0) {
@@ -145,6 +146,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             }
             CU(cudaEventRecord(ev[0], c->stream));
         }
+        dmf::expand_kernel<<<dim3((p.width + 255) / 256, p.height), 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_currx);
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_row_need);
@@ -291,6 +293,8 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_ctrl, sizeof(dmf::Ctrl)));
         CUX(cudaMalloc(&c->d_mom1, W * H * sizeof(int4)));
         CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(int2)));
+        CUX(cudaMalloc(&c->d_currx, W * H * sizeof(uint2)));
+        CUX(cudaMemsetAsync(c->d_currx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMemsetAsync(c->d_ctrl, 0, sizeof(dmf::Ctrl), c->stream));
         int per_sm = 0;
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
@@ -337,7 +341,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx);
     cudaFree(ctx->d_row_need);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

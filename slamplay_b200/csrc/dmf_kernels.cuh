@@ -104,6 +104,7 @@ struct KParams {
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
     double ti_norm;       // |t_RC| (ref:525)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
+    const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (expand_kernel)
     const uint8_t *ref;
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
     const int4 *mom1;     // per block position of the current frame: {S, cQ, cH, cV}   (moments_kernel)
@@ -338,6 +339,21 @@ __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint3
 
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
+// K2x: once per current frame — "sliding window expansion": for every position x the 8 bytes [x, x+8) of its
+// row as one aligned 64-bit word.  A sample then fetches each of its 8 block rows with ONE aligned LDG.64
+// instead of three LDG.32 + two funnel shifts; the 8x larger image stays L2-resident (16.6 MB at 1080p).
+__global__ void __launch_bounds__(256) expand_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
+                                                     uint2 *__restrict__ out) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x > width - 16 || y >= height) return;  // x <= W-16: the 12-byte row read stays inside the row
+    const uint8_t *base = img + (size_t)y * pitch + x;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
+    uint32_t lo, hi;
+    load_row8(reinterpret_cast<const uint32_t *>(base - mis), mis * 8u, lo, hi);
+    out[(size_t)y * width + x] = make_uint2(lo, hi);
+}
+
 // K2m: once per current frame — the frame-only part of every possible NCC: window sum and centred
 // Gram sums of the 8x8 block at each position (x,y) = top-left tap.  A sample whose top-left tap is
 // (bx,by) needs   mom1 at (bx,by),(bx+1,by),(bx,by+1),(bx+1,by+1)  and  mom2 at (bx,by):
@@ -446,15 +462,16 @@ struct SampleInts {
 __device__ __forceinline__ SampleInts gather_ints(const KParams &P, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
                                                   const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr, int ix,
                                                   int iy) {
-    const unsigned off = (unsigned)(iy - 3) * (unsigned)P.curr_pitch + (unsigned)(ix - 3);
-    const unsigned sh = (off & 3u) * 8u;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.curr + (size_t)(off & ~3u));
-    const int pitch_w = P.curr_pitch >> 2;
-    // gathers first (memory-level parallelism): 24 words of the block, 5 vectors of the moment table
+    // gathers first (memory-level parallelism): the 8 rows of the block (one aligned 64-bit word each, from the
+    // expanded frame), 5 vectors of the moment table
     uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) load_row8(wp + j * pitch_w, sh, lo[j], hi[j]);
     const size_t mo = (size_t)(iy - 3) * P.mom_pitch + (size_t)(ix - 3);
+    const uint2 *xp = P.currx + (size_t)(iy - 3) * P.width + (size_t)(ix - 3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint2 q = __ldg(xp + (size_t)j * P.width);
+        lo[j] = q.x; hi[j] = q.y;
+    }
     const int4 m00 = __ldg(P.mom1 + mo), m10 = __ldg(P.mom1 + mo + 1);
     const int4 m01 = __ldg(P.mom1 + mo + P.mom_pitch), m11 = __ldg(P.mom1 + mo + P.mom_pitch + 1);
     const int2 md = __ldg(P.mom2 + mo);
