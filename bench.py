@@ -52,6 +52,20 @@ def measured_peaks() -> dict:
     return {}
 
 
+def ncc_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one ncc_kernel launch from the committed ncu --set full
+    capture (profiles/r01_ncc_traffic.json): a mid-sequence launch of the 1080p workload; null for other workloads."""
+    p = ROOT / "profiles" / "r01_ncc_traffic.json"
+    try:
+        j = json.loads(p.read_text())
+        if j.get("workload") == workload:
+            return {"bytes_per_launch": j["dram_bytes_read"] + j["dram_bytes_write"], "unit": "B", "launch": "frame 40 of 299",
+                    "source": "profiles/r01_ncc_traffic.json"}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason sampler running during the timed region."""
 
@@ -135,6 +149,14 @@ def render_frames_gpu(seq, torch, device):
 
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle port / compiled reference TU) on the host cores
+def default_cpu_rows(seq, target_ncc: float) -> int:
+    """Rows of the CPU sample so that one pass costs about `target_ncc` NCC evaluations (the CPU path does
+    ~0.7 M NCC/s per core with the reference's heap allocations): ~20 NCC per pixel-update on these sequences."""
+    p = seq.params
+    per_row = (p.width - 2 * p.border) * 20.0 * (seq.n_frames - 1)
+    return max(1, int(round(target_ncc / per_row)))
+
+
 def cpu_rows_sample(p, n_rows: int):
     lo, hi = p.border, p.height - p.border
     n_rows = max(1, min(n_rows, hi - lo))
@@ -199,7 +221,7 @@ def reference_arm(args) -> dict:
         rows, stride = list(range(p.border, h - p.border)), 1
         sample = f"full {w}x{h} sequence, {seq.n_frames - 1} updates, compiled reference TU (oracle/_ref)"
     else:
-        rows, stride = cpu_rows_sample(p, args.cpu_rows or cores)
+        rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 6e6 * cores))  # ~10 s per step
         sample = (f"{len(rows)} of {h - 2 * p.border} interior rows (every {stride}th from y={rows[0]}) x all "
                   f"{seq.n_frames - 1} updates of {args.workload}; oracle port with the reference's per-NCC heap allocations")
     spec = (rows[0], stride, len(rows))
@@ -358,7 +380,7 @@ def ours(args) -> dict | None:
                 "achieved": ncc_flops_launch / (ncc_launch_ms * 1e-3) / 1e12,
                 "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                 "frac": ncc_flops_launch / (ncc_launch_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS_NOMINAL,
-                "traffic": None,
+                "traffic": ncc_traffic(args.workload),
                 "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1965 MHz); MEASURED_PEAKS.json has no FP32 figure",
                 "flop_model": "600 algorithmic FP32 flop per NCC evaluation (SURVEY.md 8d); the kernel itself computes the NCC from exact "
                               "integer moments (IDP.4A + a per-frame moment table) and is bound by L1/TEX gathers, see profiles/",
@@ -373,7 +395,7 @@ def ours(args) -> dict | None:
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"},
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (4 * n_upd + 1),
+            "gpu_launches": args.steps * (5 * n_upd + 1),  # expand, setup, moments, ncc, fuse per update + the state fill
         }
 
     # ---- end-to-end through the public API with HOST buffers ---------------------------------
@@ -487,7 +509,7 @@ def cpu_baseline_and_parity(args, seq, frames, sf, torch) -> dict:
     p = seq.params
     h, w = seq.shape
     cores = os.cpu_count() or 1
-    rows, stride = cpu_rows_sample(p, args.cpu_rows or cores)
+    rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 1.2e7 * cores))  # ~20 s
     host_frames = frames[:, :, :w].cpu().numpy()
     spec = (rows[0], stride, len(rows))
     dt, cnts, d_ref, c_ref = run_cpu_sequence(seq, host_frames, spec, heap=True, use_ref_tu=False, threads=cores)

@@ -377,12 +377,20 @@ void update_rows(const Cam &c, const Img8 &ref, const Img8 &curr, const SE3 &T,
     if (row_begin < y0) { int k = (y0 - row_begin + row_stride - 1) / row_stride; y0 = row_begin + k * row_stride; }
     long long n_rows = y1 > y0 ? (y1 - y0 + row_stride - 1) / row_stride : 0;
     unsigned long long interior = 0, active = 0, evals = 0, accepted = 0;
-#pragma omp parallel for schedule(static) reduction(+ : interior, active, evals, accepted)   // ref:356
+    // The reference parallelises over rows (ref:356).  Rows are additionally cut into column blocks here so
+    // that a ROW SUBSET (the bounded CPU-baseline sample of bench.py, fewer rows than cores) still keeps every
+    // core busy; pixels are independent, so the arithmetic per pixel is unchanged.
+    const int XB = 64;
+    const long long n_xb = (c.width - 2 * c.border + XB - 1) / XB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 1) reduction(+ : interior, active, evals, accepted)
     for (long long r = 0; r < n_rows; r++) {
+      for (long long xb = 0; xb < n_xb; xb++) {
         int y = y0 + int(r) * row_stride;
         double *drow = reinterpret_cast<double *>(reinterpret_cast<char *>(depth) + size_t(y) * dstep);
         double *crow = reinterpret_cast<double *>(reinterpret_cast<char *>(cov2) + size_t(y) * cstep);
-        for (int x = c.border; x < c.width - c.border; x++) {  // ref:363
+        const int xa = c.border + int(xb) * XB;
+        const int xe = (xa + XB < c.width - c.border) ? xa + XB : c.width - c.border;
+        for (int x = xa; x < xe; x++) {  // ref:363
             interior++;
             uint8_t fl = 0;
             if (!(crow[x] < c.min_cov || crow[x] > c.max_cov)) {  // ref:366 (NaN passes)
@@ -403,6 +411,7 @@ void update_rows(const Cam &c, const Img8 &ref, const Img8 &curr, const SE3 &T,
             }
             if (flags) flags[size_t(y) * fstep + x] = fl;
         }
+      }
     }
     if (counters) {
         counters->frames += 1;

@@ -5,19 +5,23 @@
 //   update ref:355-393, epipolarSearch ref:397-447, NCC ref:449-480,
 //   getBilinearInterpolatedValue ref:165-174, updateDepthFilter ref:482-567.
 //
-// Per frame three kernels run back to back on the context stream:
+// Per frame five kernels run back to back on the context stream:
 //
-//   setup_kernel  (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
+//   expand_kernel  (thread = position)  the 8 bytes [x, x+8) of every row position as one aligned 64-bit word,
+//                 so that a sample fetches each row of its 8x8 block with one LDG.64.
+//   setup_kernel   (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
 //                 trip count n of the l-loop ref:432.  The n samples of a pixel are cut into
 //                 work UNITS of at most CHUNK consecutive samples; units are appended to
 //                 per-length lists in HBM (length CHUNK first, ..., length 1 last).
-//   ncc_kernel    (thread = unit)  persistent CTAs pull 32-unit slices of the lists with an
+//   moments_kernel (thread = column, sliding 7-row window)  the frame-only integer moments of every
+//                 8x8 block position (see "NCC arithmetic"), for the row groups some sample reads.
+//   ncc_kernel     (thread = unit)  persistent CTAs pull 32-unit slices of the lists with an
 //                 atomic cursor, so every warp runs units of ONE length (no divergence on the
 //                 search length, which varies 0..286 per pixel) and the chip stays balanced
 //                 whatever the spatial distribution of converged / diverged pixels.  The unit's
 //                 7x7 reference patch lives in registers for all its samples; its best sample
 //                 goes to the pixel's 64-bit arg-max key with one atomicMax.
-//   fuse_kernel   (thread = pixel, FP64)  accept test ref:443, triangulation, uncertainty and
+//   fuse_kernel    (thread = pixel, FP64)  accept test ref:443, triangulation, uncertainty and
 //                 Gaussian fusion ref:482-567, in place on the HBM-resident maps.
 //
 // NCC arithmetic.  All 49 taps of one NCC share the same four bilinear weights (the tap
@@ -29,9 +33,8 @@
 //     of the block: moments_kernel computes them ONCE per frame for every block position
 //     (IDP.4A, 4 u8 MACs per instruction) into a 24 B/px table in HBM; a sample reads 5 vector
 //     loads from it instead of redoing ~136 dp4a.
-//   * the 4 cross sums need the reference patch: 56 IDP.4A per sample from aligned 32-bit
-//     __ldg gathers of the block plus funnel shifts (texture units filter with 8-bit weights and
-//     would break parity).
+//   * the 4 cross sums need the reference patch: 56 IDP.4A per sample on manual __ldg gathers of
+//     the block (texture units filter with 8-bit weights and would break parity).
 //   * the final combination (bilinear weights, w^T G w, 1/sqrt) runs in FP64 on the otherwise
 //     idle FP64 pipe, so the NCC agrees with the reference's two-pass FP64 ZNCC to ~1e-13 and
 //     the arg-max / 0.85 decisions are the reference's except for exact ties.
@@ -139,10 +142,6 @@ __device__ __forceinline__ D3 qrot(const double q[4], const D3 &v) {
     uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
     D3 c = cross3(qv, uv);
     return {v.x + q[3] * uv.x + c.x, v.y + q[3] * uv.y + c.y, v.z + q[3] * uv.z + c.z};
-}
-__device__ __forceinline__ void normalize3(D3 &a) {  // Eigen normalize(): only when squaredNorm > 0
-    double z = dot3(a, a);
-    if (z > 0) { double n = sqrt(z); a.x /= n; a.y /= n; a.z /= n; }
 }
 // normalize(px2cam(u,v)) ref:207-212,403: one reciprocal square root instead of sqrt + 3 divisions
 // (differs from the reference's divide-by-norm in the last ulp only)
