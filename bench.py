@@ -395,7 +395,7 @@ def ours(args) -> dict | None:
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"},
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (5 * n_upd + 1),  # expand, setup, moments, ncc, fuse per update + the state fill
+            "gpu_launches": args.steps * (4 * n_upd + 1),  # setup, moments, ncc, fuse per update + the state fill
         }
 
     # ---- end-to-end through the public API with HOST buffers ---------------------------------

@@ -46,7 +46,7 @@ struct dmf_ctx_impl {
     dmf::Ctrl *d_ctrl = nullptr;
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
     int2 *d_mom2 = nullptr;
-    uint2 *d_currx = nullptr;                  // expanded current frame (expand_kernel)
+    uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
     int n_pix = 0, ncc_grid = 0;
     // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
     bool timing_on = false;
@@ -146,10 +146,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             }
             CU(cudaEventRecord(ev[0], c->stream));
         }
-        dmf::expand_kernel<<<dim3((p.width + 255) / 256, p.height), 256, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_currx);
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
-        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_row_need);
+        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_currx, c->d_row_need);
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));

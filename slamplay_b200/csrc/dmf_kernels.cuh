@@ -5,16 +5,16 @@
 //   update ref:355-393, epipolarSearch ref:397-447, NCC ref:449-480,
 //   getBilinearInterpolatedValue ref:165-174, updateDepthFilter ref:482-567.
 //
-// Per frame five kernels run back to back on the context stream:
+// Per frame four kernels run back to back on the context stream:
 //
-//   expand_kernel  (thread = position)  the 8 bytes [x, x+8) of every row position as one aligned 64-bit word,
-//                 so that a sample fetches each row of its 8x8 block with one LDG.64.
 //   setup_kernel   (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
 //                 trip count n of the l-loop ref:432.  The n samples of a pixel are cut into
 //                 work UNITS of at most CHUNK consecutive samples; units are appended to
 //                 per-length lists in HBM (length CHUNK first, ..., length 1 last).
 //   moments_kernel (thread = column, sliding 7-row window)  the frame-only integer moments of every
-//                 8x8 block position (see "NCC arithmetic"), for the row groups some sample reads.
+//                 8x8 block position (see "NCC arithmetic"), for the row groups some sample reads; as a
+//                 by-product the "expanded" frame: the 8 bytes [x, x+8) of every row position as one aligned
+//                 64-bit word, so that a sample fetches each row of its 8x8 block with one LDG.64.
 //   ncc_kernel     (thread = unit)  persistent CTAs pull 32-unit slices of the lists with an
 //                 atomic cursor, so every warp runs units of ONE length (no divergence on the
 //                 search length, which varies 0..286 per pixel) and the chip stays balanced
@@ -107,7 +107,7 @@ struct KParams {
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
     double ti_norm;       // |t_RC| (ref:525)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
-    const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (expand_kernel)
+    const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (moments_kernel)
     const uint8_t *ref;
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
     const int4 *mom1;     // per block position of the current frame: {S, cQ, cH, cV}   (moments_kernel)
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
                 const double ya = fma(-half, ly, pmy), yb = fma(half, ly, pmy);
                 const double ylo = fmin(ya, yb), yhi = fmax(ya, yb);
                 need_lo = max((int)fmax(ylo, (double)P.border) - 3, 0);
-                need_hi = min((int)fmin(yhi, (double)(P.height - P.border)) - 2, P.height - 1);
+                need_hi = min((int)fmin(yhi, (double)(P.height - P.border)) - 2 + 6, P.height - 1);  // +6: block rows iy-3..iy+4 of the expanded frame
             }
             const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
             PixelRec *rec = P.rec + pidx;  // four 16-byte vector stores
@@ -338,21 +338,6 @@ __device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint3
 
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
-// K2x: once per current frame — "sliding window expansion": for every position x the 8 bytes [x, x+8) of its
-// row as one aligned 64-bit word.  A sample then fetches each of its 8 block rows with ONE aligned LDG.64
-// instead of three LDG.32 + two funnel shifts; the 8x larger image stays L2-resident (16.6 MB at 1080p).
-__global__ void __launch_bounds__(256) expand_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
-                                                     uint2 *__restrict__ out) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x > width - 16 || y >= height) return;  // x <= W-16: the 12-byte row read stays inside the row
-    const uint8_t *base = img + (size_t)y * pitch + x;
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u);
-    uint32_t lo, hi;
-    load_row8(reinterpret_cast<const uint32_t *>(base - mis), mis * 8u, lo, hi);
-    out[(size_t)y * width + x] = make_uint2(lo, hi);
-}
-
 // K2m: once per current frame — the frame-only part of every possible NCC: window sum and centred
 // Gram sums of the 8x8 block at each position (x,y) = top-left tap.  A sample whose top-left tap is
 // (bx,by) needs   mom1 at (bx,by),(bx+1,by),(bx,by+1),(bx+1,by+1)  and  mom2 at (bx,by):
@@ -372,11 +357,11 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint8_t *__restrict__
 constexpr int MOM_STRIP = DMF_MOM_STRIP;
 constexpr int MOM_THREADS = DMF_MOM_THREADS;
 
-struct RowBytes { uint32_t x0l, x0h, x1l, x1h; };  // columns 0..6 (x0) and 1..7 (x1) of one block row
+struct RowBytes { uint32_t x0l, x0h, x1l, x1h, hi; };  // columns 0..6 (x0) and 1..7 (x1) of one block row; hi = bytes 4..7
 __device__ __forceinline__ RowBytes load_row_bytes(const uint32_t *wp, unsigned sh) {
     uint32_t lo, hi;
     load_row8(wp, sh, lo, hi);
-    return {lo, hi & 0x00FFFFFFu, __funnelshift_r(lo, hi, 8), hi >> 8};
+    return {lo, hi & 0x00FFFFFFu, __funnelshift_r(lo, hi, 8), hi >> 8, hi};
 }
 struct RowSums { int s0, s1, q, h; };  // one row: sum cols 0..6, sum cols 1..7, sum of squares cols 0..6, neighbour products
 __device__ __forceinline__ RowSums row_sums(const RowBytes &r) {
@@ -392,7 +377,7 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
 
 __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                       int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch,
-                                                      const uint8_t *__restrict__ row_need) {
+                                                      uint2 *__restrict__ currx, const uint8_t *__restrict__ row_need) {
     const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
     const int y0 = blockIdx.y * MOM_STRIP;
     const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
@@ -435,6 +420,10 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
         b.y = NCC_AREA * D2 - S1 * S0n;
         mom1[(size_t)y * mom_pitch + x] = a;
         mom2[(size_t)y * mom_pitch + x] = b;
+        // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
+        // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
+        // funnel shifts (the 8x larger frame stays L2-resident: 16.6 MB at 1080p)
+        currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
         // advance the window to position y+1
         S0 = S0n; S1 = S1n;
         Q += rn.q - ro.q; H += rn.h - ro.h;
