@@ -6,6 +6,7 @@ There is no CPU or PyTorch fallback for the depth-filter path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -105,7 +106,8 @@ def _bind(lib: C.CDLL, table: dict) -> None:
 def load_dmf() -> C.CDLL:
     """Load slamplay_b200/libdmf.so (CUDA, sm_100a).  Raises if it is not built."""
     if "dmf" not in _cache:
-        path = PKG / "libdmf.so"
+        # DMF_LIB: development override (A/B runs of kernel variants built by tools/build_variants.sh)
+        path = Path(os.environ["DMF_LIB"]) if os.environ.get("DMF_LIB") else PKG / "libdmf.so"
         if not path.exists():
             raise RuntimeError(
                 f"{path} is missing: build it with `python -m slamplay_b200.build` "

@@ -47,6 +47,7 @@ struct dmf_ctx_impl {
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
     int2 *d_mom2 = nullptr;
     uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
+    uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
     // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
     bool timing_on = false;
@@ -97,7 +98,7 @@ int check_params(const dmf_params *p, std::string &why) {
     if (p->width < 64 || p->height < 64 || p->width > 32768 || p->height > 32768) { why = "width/height out of range [64,32768]"; return -1; }
     if (p->ncc_half != 3) { why = "only ncc_half == 3 (7x7 window, ref:79) is supported"; return -1; }
     if (p->border < 4 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 4 and < min(width,height)/2"; return -1; }
-    // the work-unit encoding holds chunk indices < 64 (CHUNK = 8 samples): trip count < 512
+    // the arg-max key holds sample indices < 510 (KEY_IDX_BITS = 9); the work-unit encoding chunk indices < 64
     if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 250.0)) { why = "step must be > 0 and max_half_len/step <= 250"; return -1; }
     if ((long long)(p->width - 2 * p->border) * (p->height - 2 * p->border) >= (1ll << 26)) { why = "more than 2^26 interior pixels"; return -1; }
     if (!(p->fx != 0) || !(p->fy != 0)) { why = "fx, fy must be non-zero"; return -1; }
@@ -120,8 +121,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     for (int i = 0; i < 3; ++i) K.t[i] = t[i];
     se3_inverse(q, t, K.qi, K.ti);
     K.ti_norm = std::sqrt(K.ti[0] * K.ti[0] + (K.ti[1] * K.ti[1] + K.ti[2] * K.ti[2]));
+    K.bd = (double)p.border; K.wd = (double)p.width; K.hd = (double)p.height;
     K.inv_fx = 1.0 / p.fx; K.inv_fy = 1.0 / p.fy; K.inv_step = 1.0 / p.step;
-    K.curr = d_curr; K.ref = c->d_ref; K.refstat = c->d_refstat;
+    K.curr = d_curr; K.ref = c->d_ref; K.refx = c->d_refx; K.refstat = c->d_refstat;
     K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
     K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
     K.flags_pitch = p.width;
@@ -294,6 +296,8 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(int2)));
         CUX(cudaMalloc(&c->d_currx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_currx, 0, W * H * sizeof(uint2), c->stream));
+        CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));
+        CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMemsetAsync(c->d_ctrl, 0, sizeof(dmf::Ctrl), c->stream));
         int per_sm = 0;
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
@@ -340,7 +344,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx); cudaFree(ctx->d_refx);
     cudaFree(ctx->d_row_need);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -366,6 +370,7 @@ static int run_ref_stats(dmf_ctx *c) {
     dim3 blk(32, 8);
     dim3 grid((p.width - 2 * p.border + 31) / 32, (p.height - 2 * p.border + 7) / 8);
     dmf::ref_stats_kernel<<<grid, blk, 0, c->stream>>>(c->d_ref, c->img_pitch, p.width, p.height, p.border, c->d_refstat, p.width);
+    dmf::ref_expand_kernel<<<dim3((p.width + 255) / 256, p.height), 256, 0, c->stream>>>(c->d_ref, c->img_pitch, p.width, p.height, c->d_refx);
     CU(cudaGetLastError());
     c->have_ref = true;
     return DMF_OK;

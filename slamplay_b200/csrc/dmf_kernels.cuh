@@ -5,6 +5,7 @@
 //   update ref:355-393, epipolarSearch ref:397-447, NCC ref:449-480,
 //   getBilinearInterpolatedValue ref:165-174, updateDepthFilter ref:482-567.
 //
+// Once per reference frame: ref_stats_kernel (patch sums) and ref_expand_kernel (7-byte rows as aligned 64-bit words).
 // Per frame four kernels run back to back on the context stream:
 //
 //   setup_kernel   (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
@@ -15,7 +16,7 @@
 //                 8x8 block position (see "NCC arithmetic"), for the row groups some sample reads; as a
 //                 by-product the "expanded" frame: the 8 bytes [x, x+8) of every row position as one aligned
 //                 64-bit word, so that a sample fetches each row of its 8x8 block with one LDG.64.
-//   ncc_kernel     (thread = unit)  persistent CTAs pull 32-unit slices of the lists with an
+//   ncc_kernel     (thread = unit)  persistent CTAs pull 64-unit grabs of the lists with an
 //                 atomic cursor, so every warp runs units of ONE length (no divergence on the
 //                 search length, which varies 0..286 per pixel) and the chip stays balanced
 //                 whatever the spatial distribution of converged / diverged pixels.  The unit's
@@ -52,16 +53,22 @@ namespace dmf {
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 8;
 constexpr int TILE_PIX = TILE_W * TILE_H;
-constexpr int CHUNK = 8;          // samples per work unit
+#ifndef DMF_CHUNK
+#define DMF_CHUNK 16
+#endif
+#ifndef DMF_GRAB
+#define DMF_GRAB 64
+#endif
+constexpr int CHUNK = DMF_CHUNK;  // samples per work unit
 constexpr int CHUNK_BITS = 6;     // unit = (pixel index << CHUNK_BITS) | chunk index   (chunk < 64)
 #ifndef DMF_NCC_THREADS
-#define DMF_NCC_THREADS 256
+#define DMF_NCC_THREADS 192
 #endif
 #ifndef DMF_NCC_MIN_BLOCKS
-#define DMF_NCC_MIN_BLOCKS 2
+#define DMF_NCC_MIN_BLOCKS 3
 #endif
 constexpr int NCC_THREADS = DMF_NCC_THREADS;
-constexpr int GRAB = 64;          // units a warp pulls per atomic
+constexpr int GRAB = DMF_GRAB;    // units a warp pulls per atomic
 constexpr int NCC_AREA = 49;
 // 1e-10 * (49*255^2)^2 : the reference's epsilon (ref:479) in centred-integer units
 constexpr double NCC_EPS_INT = 1015.2029750625;
@@ -106,9 +113,11 @@ struct KParams {
     double q[4], t[3];    // T_C_R (unit quaternion x,y,z,w + translation)
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
     double ti_norm;       // |t_RC| (ref:525)
+    double bd, wd, hd;    // border, width, height as doubles (inside() ref:222-224 without per-sample I2F)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
     const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (moments_kernel)
     const uint8_t *ref;
+    const uint2 *refx;    // expanded reference frame: refx[y*width + x] = bytes ref[y][x-3 .. x+3], 0   (ref_expand_kernel)
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
     const int4 *mom1;     // per block position of the current frame: {S, cQ, cH, cV}   (moments_kernel)
     const int2 *mom2;     //                                          {cD1, cD2}
@@ -195,6 +204,19 @@ __global__ void __launch_bounds__(256) ref_stats_kernel(const uint8_t *__restric
         }
     }
     stat[(size_t)y * stat_pitch + x] = make_int2(s, NCC_AREA * s2 - s * s);
+}
+
+// Once per reference frame: the 7 bytes [x-3, x+3] of every row position as one aligned 64-bit word (8th byte 0), so
+// that a work unit fetches each row of its 7x7 reference patch with ONE aligned LDG.64 and no funnel shifts.
+__global__ void __launch_bounds__(256) ref_expand_kernel(const uint8_t *__restrict__ ref, int ref_pitch, int width, int height,
+                                                         uint2 *__restrict__ refx) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < 3 || x + 3 >= width || y >= height) return;
+    const uint8_t *row = ref + (size_t)y * ref_pitch + (x - 3);
+    const uint32_t lo = row[0] | (row[1] << 8) | (row[2] << 16) | ((uint32_t)row[3] << 24);
+    const uint32_t hi = row[4] | (row[5] << 8) | (row[6] << 16);
+    refx[(size_t)y * width + x] = make_uint2(lo, hi);
 }
 
 __device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v) {
@@ -447,45 +469,6 @@ struct SampleInts {
     int cR00, cR10, cR01, cR11;                                                // 49*R - Sr*S per window
     int g0000, g1010, g0101, g1111, g0010, g0111, g0001, g1011, g0011, g1001;  // 49*G - S*S'
 };
-__device__ __forceinline__ SampleInts gather_ints(const KParams &P, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
-                                                  const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr, int ix,
-                                                  int iy) {
-    // gathers first (memory-level parallelism): the 8 rows of the block (one aligned 64-bit word each, from the
-    // expanded frame), 5 vectors of the moment table
-    uint32_t lo[8], hi[8];
-    const size_t mo = (size_t)(iy - 3) * P.mom_pitch + (size_t)(ix - 3);
-    const uint2 *xp = P.currx + (size_t)(iy - 3) * P.width + (size_t)(ix - 3);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint2 q = __ldg(xp + (size_t)j * P.width);
-        lo[j] = q.x; hi[j] = q.y;
-    }
-    const int4 m00 = __ldg(P.mom1 + mo), m10 = __ldg(P.mom1 + mo + 1);
-    const int4 m01 = __ldg(P.mom1 + mo + P.mom_pitch), m11 = __ldg(P.mom1 + mo + P.mom_pitch + 1);
-    const int2 md = __ldg(P.mom2 + mo);
-    // cross sums with the reference patch: window (a,b) = block columns a..a+6, rows b..b+6
-    int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (j > 0) {
-            R01 = dp4(R0lo[j - 1], lo[j], dp4(R0hi[j - 1], hi[j], R01));
-            R11 = dp4(R1lo[j - 1], lo[j], dp4(R1hi[j - 1], hi[j], R11));
-        }
-        if (j < 7) {
-            R00 = dp4(R0lo[j], lo[j], dp4(R0hi[j], hi[j], R00));
-            R10 = dp4(R1lo[j], lo[j], dp4(R1hi[j], hi[j], R10));
-        }
-    }
-    SampleInts s;
-    // exact centring in int32 (all terms < 2^31)
-    s.cR00 = NCC_AREA * R00 + nSr * m00.x; s.cR10 = NCC_AREA * R10 + nSr * m10.x;
-    s.cR01 = NCC_AREA * R01 + nSr * m01.x; s.cR11 = NCC_AREA * R11 + nSr * m11.x;
-    s.g0000 = m00.y; s.g1010 = m10.y; s.g0101 = m01.y; s.g1111 = m11.y;
-    s.g0010 = m00.z; s.g0111 = m01.z; s.g0001 = m00.w; s.g1011 = m10.w;
-    s.g0011 = md.x; s.g1001 = md.y;
-    return s;
-}
-
 // The FP64 part: combination with the bilinear weights of ref:169-172 (fractions fx, fy, ref:167-168);
 // den1 = 49*sum r^2 - (sum r)^2.  int -> double conversions run on the XU pipe (I2F.F64), idle otherwise.
 __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, double fx, double fy) {
@@ -510,6 +493,83 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
 }
 
 // K2b: NCC over the work units.
+
+// One sample's memory operands: the 8 rows of the 8x8 block (one aligned 64-bit word each, from the expanded frame)
+// and 5 vectors of the moment table.  All loads are issued before the first use (memory-level parallelism).
+struct RawSample {
+    uint32_t lo[8], hi[8];
+    int4 m00, m10, m01, m11;
+    int2 md;
+};
+__device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSample &r) {
+    // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
+    const unsigned o = (unsigned)(iy - 3) * (unsigned)P.width + (unsigned)(ix - 3);
+    const uint2 *xp = P.currx + o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint2 q = __ldg(xp + (size_t)j * (unsigned)P.width);
+        r.lo[j] = q.x; r.hi[j] = q.y;
+    }
+    const int4 *m1 = P.mom1 + o;
+    r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1);
+    r.m01 = __ldg(m1 + (unsigned)P.width); r.m11 = __ldg(m1 + (unsigned)P.width + 1);
+    r.md = __ldg(P.mom2 + o);
+}
+// cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring
+__device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
+                                                 const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr) {
+    int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j > 0) {
+            R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
+            R11 = dp4(R1lo[j - 1], r.lo[j], dp4(R1hi[j - 1], r.hi[j], R11));
+        }
+        if (j < 7) {
+            R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
+            R10 = dp4(R1lo[j], r.lo[j], dp4(R1hi[j], r.hi[j], R10));
+        }
+    }
+    SampleInts s;
+    // exact centring in int32 (all terms < 2^31)
+    s.cR00 = NCC_AREA * R00 + nSr * r.m00.x; s.cR10 = NCC_AREA * R10 + nSr * r.m10.x;
+    s.cR01 = NCC_AREA * R01 + nSr * r.m01.x; s.cR11 = NCC_AREA * R11 + nSr * r.m11.x;
+    s.g0000 = r.m00.y; s.g1010 = r.m10.y; s.g0101 = r.m01.y; s.g1111 = r.m11.y;
+    s.g0010 = r.m00.z; s.g0111 = r.m01.z; s.g0001 = r.m00.w; s.g1011 = r.m10.w;
+    s.g0011 = r.md.x; s.g1001 = r.md.y;
+    return s;
+}
+// integer part and fraction of a sample coordinate c (0 <= c < 2^31), ref:167-168.  Adding 2^52 with round-down
+// leaves floor(c) in the low mantissa word: DADDs on the FP64 pipe instead of F2I + I2F on the eighth-rate XU pipe.
+__device__ __forceinline__ void split_coord(double c, int &i, double &f) {
+    const double t = __dadd_rd(c, 4503599627370496.0);
+    i = __double2loint(t);
+    f = c - (t - 4503599627370496.0);
+}
+
+// Descriptors of the GRAB/32 slices at cursor value g (warp-uniform): unit words and their common length.
+__device__ __forceinline__ void fetch_units(const KParams &P, const unsigned (&counts)[CHUNK + 1], unsigned total, unsigned g,
+                                            int lane, unsigned (&units)[GRAB / 32], int (&lens)[GRAB / 32]) {
+#pragma unroll
+    for (int sub = 0; sub < GRAB / 32; ++sub) {
+        const unsigned w0 = g + sub * 32;  // warp-uniform slot base (32-aligned)
+        // segment of this slice (uniform): unit length L, first slot, number of units
+        int L = 0;
+        unsigned start = 0, cnt = 0, acc = 0;
+#pragma unroll
+        for (int c = CHUNK; c >= 1; --c) {
+            const unsigned padded = (counts[c] + 31u) & ~31u;
+            if (w0 >= acc && w0 < acc + padded) { L = c; start = acc; cnt = counts[c]; }
+            acc += padded;
+        }
+        const unsigned idx = w0 - start + lane;
+        const bool valid = (w0 < total) && (idx < cnt);
+        lens[sub] = valid ? L : 0;
+        units[sub] = 0;
+        if (valid) units[sub] = (L == CHUNK) ? __ldg(P.units_full + idx) : __ldg(P.units_tail + (size_t)(L - 1) * P.n_pix + idx);
+    }
+}
+
 __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
     const int lane = threadIdx.x & 31;
     // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
@@ -530,24 +590,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
         // descriptors of all GRAB/32 slices first: their latency overlaps instead of heading every slice
         unsigned units[GRAB / 32];
         int lens[GRAB / 32];
-#pragma unroll
-        for (int sub = 0; sub < GRAB / 32; ++sub) {
-            const unsigned w0 = g + sub * 32;  // warp-uniform slot base (32-aligned)
-            // segment of this slice (uniform): unit length L, first slot, number of units
-            int L = 0;
-            unsigned start = 0, cnt = 0, acc = 0;
-#pragma unroll
-            for (int c = CHUNK; c >= 1; --c) {
-                const unsigned padded = (counts[c] + 31u) & ~31u;
-                if (w0 >= acc && w0 < acc + padded) { L = c; start = acc; cnt = counts[c]; }
-                acc += padded;
-            }
-            const unsigned idx = w0 - start + lane;
-            const bool valid = (w0 < total) && (idx < cnt);
-            lens[sub] = valid ? L : 0;
-            units[sub] = 0;
-            if (valid) units[sub] = (L == CHUNK) ? __ldg(P.units_full + idx) : __ldg(P.units_tail + (size_t)(L - 1) * P.n_pix + idx);
-        }
+        fetch_units(P, counts, total, g, lane, units, lens);
 #pragma unroll
         for (int sub = 0; sub < GRAB / 32; ++sub) {
             const int L = lens[sub];
@@ -565,29 +608,24 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             const double den1 = (double)hv.w;
             const int x = xy.x, y = xy.y;
 
-            // reference patch of (x,y) into registers
+            // reference patch of (x,y) into registers: 7 aligned 64-bit words of the expanded reference frame
             uint32_t R0lo[7], R0hi[7], R1lo[7], R1hi[7];
             {
-                const unsigned off = (unsigned)(y - 3) * (unsigned)P.ref_pitch + (unsigned)(x - 3);
-                const unsigned sh = (off & 3u) * 8u;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.ref + (size_t)(off & ~3u));
-                const int pw = P.ref_pitch >> 2;
+                const uint2 *rp = P.refx + (unsigned)(y - 3) * (unsigned)P.width + (unsigned)x;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) {
-                    uint32_t a, b;
-                    load_row8(wp + j * pw, sh, a, b);
-                    b &= 0x00FFFFFFu;
-                    R0lo[j] = a; R0hi[j] = b;
-                    R1lo[j] = a << 8; R1hi[j] = __funnelshift_l(a, b, 8);
+                    const uint2 q = __ldg(rp + (size_t)j * (unsigned)P.width);
+                    R0lo[j] = q.x; R0hi[j] = q.y;
+                    R1lo[j] = q.x << 8; R1hi[j] = __funnelshift_l(q.x, q.y, 8);
                 }
             }
 
             double best_v = -1.0;  // ref:430
             int best_k = -1;
-            int pix = -1, piy = -1;  // integer position whose SampleInts are held
+            int hix = -1, hiy = -1;  // integer position whose SampleInts are held
             SampleInts si{};
             // position of the first sample; inside the loop the position of sample j+1 is computed
-            // before the NCC of sample j so its FP64 -> int chain is off the critical path
+            // before the NCC of sample j so its FP64 chain is off the critical path
             double sx, sy;
             {
                 const double l = sample_l(half, P.step, k0);
@@ -603,14 +641,19 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                     sy = fma(l, dir.y, pm.y);
                 }
                 // inside() ref:222-224
-                const bool ok = cx >= P.border && cy >= P.border && cx + P.border < P.width && cy + P.border <= P.height;
+                const bool ok = cx >= P.bd && cy >= P.bd && cx + P.bd < P.wd && cy + P.bd <= P.hd;
                 if (!ok) continue;
-                const int ix = (int)cx, iy = (int)cy;  // positive: trunc == floor
-                if (ix != pix || iy != piy) {
-                    si = gather_ints(P, R0lo, R0hi, R1lo, R1hi, nSr, ix, iy);
-                    pix = ix; piy = iy;
+                int ix, iy;
+                double fx, fy;
+                split_coord(cx, ix, fx);
+                split_coord(cy, iy, fy);
+                if (ix != hix || iy != hiy) {
+                    RawSample raw;
+                    load_raw(P, ix, iy, raw);
+                    si = reduce_raw(raw, R0lo, R0hi, R1lo, R1hi, nSr);
+                    hix = ix; hiy = iy;
                 }
-                const double v = ncc_combine(si, den1, cx - (double)ix, cy - (double)iy);
+                const double v = ncc_combine(si, den1, fx, fy);
                 ++my_evals;
                 if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
