@@ -43,7 +43,9 @@ struct dmf_ctx_impl {
     dmf::PixelRec *d_rec = nullptr;            // n_pix 64-byte records
     unsigned long long *d_best = nullptr;
     unsigned int *d_units_full = nullptr, *d_units_tail = nullptr;
-    dmf::Ctrl *d_ctrl = nullptr;
+    dmf::Ctrl *d_ctrl = nullptr;               // two control blocks: frame k uses [k & 1], fuse_kernel re-arms the other
+    double2 *d_state_c = nullptr;              // per slot: (depth, cov2) as setup_kernel read them
+    unsigned long long ctrl_idx = 0;
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
     int2 *d_mom2 = nullptr;
     uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
@@ -131,7 +133,8 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.n_pix = c->n_pix;
     K.rec = c->d_rec;
     K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width; K.currx = c->d_currx;
-    K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.ctrl = c->d_ctrl;
+    K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.state_c = c->d_state_c;
+    K.ctrl = c->d_ctrl + (c->ctrl_idx & 1); K.ctrl_next = c->d_ctrl + ((c->ctrl_idx + 1) & 1);
     const int rows = c->n_rows;
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
@@ -154,9 +157,10 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
-        dmf::fuse_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        dmf::fuse_kernel<<<(c->n_pix + dmf::TILE_PIX - 1) / dmf::TILE_PIX, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
         CU(cudaGetLastError());
+        c->ctrl_idx++;
     }
     c->frames++;
     return DMF_OK;
@@ -291,14 +295,15 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_best, np * sizeof(unsigned long long)));
         CUX(cudaMalloc(&c->d_units_full, np * max_full * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
-        CUX(cudaMalloc(&c->d_ctrl, sizeof(dmf::Ctrl)));
+        CUX(cudaMalloc(&c->d_ctrl, 2 * sizeof(dmf::Ctrl)));
+        CUX(cudaMalloc(&c->d_state_c, np * sizeof(double2)));
         CUX(cudaMalloc(&c->d_mom1, W * H * sizeof(int4)));
         CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(int2)));
         CUX(cudaMalloc(&c->d_currx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_currx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
-        CUX(cudaMemsetAsync(c->d_ctrl, 0, sizeof(dmf::Ctrl), c->stream));
+        CUX(cudaMemsetAsync(c->d_ctrl, 0, 2 * sizeof(dmf::Ctrl), c->stream));
         int per_sm = 0;
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
@@ -344,7 +349,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx); cudaFree(ctx->d_refx);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_state_c); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx); cudaFree(ctx->d_refx);
     cudaFree(ctx->d_row_need);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -77,13 +77,14 @@ constexpr unsigned KEY_SENTINEL_LO = 511u;
 
 // Per-frame control block in HBM.
 struct Ctrl {
-    unsigned int count[CHUNK + 1];  // count[L] = number of units of length L (L = 1..CHUNK)
+    unsigned int count[CHUNK + 1];  // count[L] = number of units of length L (L = 1..CHUNK); count[0] = active pixels
     unsigned int cursor;            // next unclaimed slot of the padded, concatenated lists
     unsigned int pad[6];
 };
 
-// Per-pixel record of one frame (64 B = half a cache line, four 16-byte vectors): everything
-// ncc_kernel / fuse_kernel need about an active pixel, so a work unit starts with ONE line fetch.
+// Record of one ACTIVE pixel of one frame (64 B = half a cache line, four 16-byte vectors): everything
+// ncc_kernel / fuse_kernel need about it, so a work unit starts with ONE line fetch.  Records are compacted:
+// setup_kernel gives every active pixel a slot (CTA-aggregated counter), units and fuse_kernel address slots.
 struct __align__(16) PixelRec {
     double2 pm;        // px_mean_curr ref:406
     double2 dir;       // epipolar_direction ref:419-420
@@ -123,12 +124,14 @@ struct KParams {
     const int2 *mom2;     //                                          {cD1, cD2}
     double *depth;
     double *cov2;
-    // per-frame scratch, indexed by the band-local interior pixel index
-    PixelRec *rec;                                 // written by setup_kernel for active pixels
+    // per-frame scratch, indexed by the slot of the active pixel (compacted by setup_kernel)
+    PixelRec *rec;                                 // written by setup_kernel
+    double2 *state_c;                              // (depth, cov2) of the slot's pixel as setup_kernel read them
     unsigned long long *best;                      // arg-max keys
     unsigned int *units_full;                      // units of length CHUNK
     unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
-    Ctrl *ctrl;
+    Ctrl *ctrl;                                    // this frame's control block
+    Ctrl *ctrl_next;                               // the next frame's (re-armed by fuse_kernel)
     uint8_t *row_need;                             // [height/8 + 1]: 8-row groups of the moment table some sample reads
     uint8_t *flags;
     float *dbg_ncc;  // with write_flags: best NCC per active pixel (rounded to f32)
@@ -256,7 +259,7 @@ __device__ __forceinline__ void search_geometry(const KParams &P, int x, int y, 
 }
 
 // ----------------------------------------------------------------------------------------
-// K2a: per-pixel setup + work-unit emission.
+// K2a: per-pixel setup + compaction of the active pixels + work-unit emission.
 __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__ KParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -264,18 +267,17 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
     const bool in_img = (x < P.width - P.border) && (rl < P.n_rows);
     const int y = row_of(P, rl);
-    const int pidx = rl * P.wi + (x - P.border);
 
     int n = 0;
     bool active = false;
     int need_lo = 0x7fffffff, need_hi = -1;  // moment-table rows this pixel's samples read
+    double mu = 0, c2 = 0, pmx = 0, pmy = 0, lx = 0, ly = 0, half = 0;
+    int2 st = make_int2(0, 0);
     if (in_img) {
-        const double c2 = P.cov2[(size_t)y * P.state_pitch + x];
-        const double mu = P.depth[(size_t)y * P.state_pitch + x];  // issued with the cov load: one round trip
+        c2 = P.cov2[(size_t)y * P.state_pitch + x];
+        mu = P.depth[(size_t)y * P.state_pitch + x];  // issued with the cov load: one round trip
         active = !(c2 < P.min_cov || c2 > P.max_cov);  // ref:366 — NaN passes the gate
-        P.best[pidx] = key_init();
         if (active) {
-            double pmx, pmy, lx, ly, half;
             search_geometry(P, x, y, mu, c2, pmx, pmy, lx, ly, half);
             // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
             if (half >= 0) {
@@ -290,22 +292,21 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
                 need_lo = max((int)fmax(ylo, (double)P.border) - 3, 0);
                 need_hi = min((int)fmin(yhi, (double)(P.height - P.border)) - 2 + 6, P.height - 1);  // +6: block rows iy-3..iy+4 of the expanded frame
             }
-            const int2 st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
-            PixelRec *rec = P.rec + pidx;  // four 16-byte vector stores
-            rec->pm = make_double2(pmx, pmy);
-            rec->dir = make_double2(lx, ly);
-            *reinterpret_cast<int4 *>(&rec->half) = make_int4(__double2loint(half), __double2hiint(half), -st.x, st.y);
-            rec->xy = make_int4(x, y, 0, 0);
+            st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
         }
-        if (P.write_flags) P.dbg_n[(size_t)y * P.flags_pitch + x] = n;
+        if (P.write_flags) {  // debug planes: fuse_kernel only visits active pixels
+            const size_t o = (size_t)y * P.flags_pitch + x;
+            P.dbg_n[o] = n;
+            if (!active) { P.flags[o] = 0; P.dbg_ncc[o] = 0.0f; }
+        }
     }
 
-    // ---- emit work units.  List space is claimed once per CTA and per list (thread L does the
-    // atomicAdd for list L, so its latency is paid once per CTA instead of by every warp); every warp
-    // then writes its units chunk-major so that adjacent slots hold adjacent pixels of one image row.
+    // ---- slots and work units.  Space is claimed once per CTA and per list (thread L does the atomicAdd for list L,
+    // thread 0 the one for the active-pixel slots, so the latency is paid once per CTA instead of by every warp);
+    // every warp then writes its units chunk-major so that adjacent list entries hold adjacent pixels of one image row.
     __shared__ int s_need_lo, s_need_hi;                   // moment-table rows the CTA's samples read
-    __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units)
-    __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first slot of that warp in list L
+    __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
+    __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first entry of that warp in list L / first slot
     const int warp = tid >> 5;
     if (tid == 0) { s_need_lo = 0x7fffffff; s_need_hi = -1; }
     __syncthreads();
@@ -324,9 +325,10 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
         if (lane == L) s_cnt[warp][L] = (unsigned)__popc(bal);
         if (tail == L) my_rank = (unsigned)__popc(bal & lt_mask);
     }
-    if (lane == 0) s_cnt[warp][CHUNK] = (unsigned)tot_full;
+    const unsigned act_bal = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) { s_cnt[warp][CHUNK] = (unsigned)tot_full; s_cnt[warp][0] = (unsigned)__popc(act_bal); }
     __syncthreads();
-    if (tid >= 1 && tid <= CHUNK) {
+    if (tid <= CHUNK) {
         unsigned pre[TILE_PIX / 32], tot = 0;
 #pragma unroll
         for (int w = 0; w < TILE_PIX / 32; ++w) { pre[w] = tot; tot += s_cnt[w][tid]; }
@@ -338,16 +340,26 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     // mark the 8-row groups of the moment table this CTA's samples read (moments_kernel skips the others)
     if (s_need_hi >= s_need_lo)
         for (int g = (s_need_lo >> 3) + tid; g <= (s_need_hi >> 3); g += TILE_PIX) P.row_need[g] = 1;
+    const unsigned slot = s_base[warp][0] + (unsigned)__popc(act_bal & lt_mask);
+    if (active) {
+        PixelRec *rec = P.rec + slot;  // four 16-byte vector stores
+        rec->pm = make_double2(pmx, pmy);
+        rec->dir = make_double2(lx, ly);
+        *reinterpret_cast<int4 *>(&rec->half) = make_int4(__double2loint(half), __double2hiint(half), -st.x, st.y);
+        rec->xy = make_int4(x, y, 0, 0);
+        P.state_c[slot] = make_double2(mu, c2);
+        P.best[slot] = key_init();
+    }
     if (m_full > 0) {
         unsigned base = s_base[warp][CHUNK];
         for (int j = 0; j < m_full; ++j) {
             const unsigned bal = __ballot_sync(0xffffffffu, n_full > j);
-            if (n_full > j) P.units_full[base + __popc(bal & lt_mask)] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)j;
+            if (n_full > j) P.units_full[base + __popc(bal & lt_mask)] = (slot << CHUNK_BITS) | (unsigned)j;
             base += __popc(bal);
         }
     }
     if (tail > 0)
-        P.units_tail[(size_t)(tail - 1) * P.n_pix + s_base[warp][tail] + my_rank] = ((unsigned)pidx << CHUNK_BITS) | (unsigned)n_full;
+        P.units_tail[(size_t)(tail - 1) * P.n_pix + s_base[warp][tail] + my_rank] = (slot << CHUNK_BITS) | (unsigned)n_full;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -596,10 +608,10 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             const int L = lens[sub];
             if (L == 0) continue;
             const unsigned unit = units[sub];
-            const int pidx = (int)(unit >> CHUNK_BITS);
+            const unsigned slot = unit >> CHUNK_BITS;
             const int k0 = (int)(unit & ((1u << CHUNK_BITS) - 1u)) * CHUNK;
             // one 64-byte record fetch
-            const PixelRec *rec = P.rec + pidx;
+            const PixelRec *rec = P.rec + slot;
             const double2 pm = rec->pm, dir = rec->dir;
             const int4 hv = *reinterpret_cast<const int4 *>(&rec->half);
             const int4 xy = rec->xy;
@@ -657,7 +669,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 ++my_evals;
                 if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
-            if (best_k >= 0) atomicMax(&P.best[pidx], ncc_key(best_v, best_k));
+            if (best_k >= 0) atomicMax(&P.best[slot], ncc_key(best_v, best_k));
         }
     }
 #pragma unroll
@@ -666,107 +678,96 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
 }
 
 // ----------------------------------------------------------------------------------------
-// K2c: accept test + depth-filter fusion, in place.  Also re-arms the control block.
+// K2c: accept test + depth-filter fusion over the compacted active pixels (thread = slot), in place on the maps.
+// Key, record and the state setup_kernel read arrive in ONE round trip.  Also re-arms the next frame's control block.
 #ifndef DMF_FUSE_MIN_BLOCKS
 #define DMF_FUSE_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(const __grid_constant__ KParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
-    const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
-    const bool in_img = (x < P.width - P.border) && (rl < P.n_rows);
-    const int y = row_of(P, rl);
-    const int pidx = rl * P.wi + (x - P.border);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) {
-        reinterpret_cast<unsigned *>(P.ctrl)[tid] = 0;  // ncc_kernel of this frame is done (stream order)
+    const unsigned n_active = P.ctrl->count[0];
+    if (blockIdx.x == 0) {
+        if (tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) reinterpret_cast<unsigned *>(P.ctrl_next)[tid] = 0;
+        for (int r = tid; r < P.height / 8 + 1; r += TILE_PIX) P.row_need[r] = 0;  // ncc_kernel / moments_kernel of this frame are done
+        if (tid == 0 && n_active) atomicAdd(&P.counters[0], (unsigned long long)n_active);
     }
-    if (blockIdx.y == 0) {  // re-arm the row flags for the next frame
-        for (int r = blockIdx.x * TILE_PIX + tid; r < P.height / 8 + 1; r += gridDim.x * TILE_PIX) P.row_need[r] = 0;
-    }
+    const unsigned slot = blockIdx.x * TILE_PIX + tid;
+    if (blockIdx.x * TILE_PIX >= n_active) return;  // CTA-uniform
+    const bool active = slot < n_active;
 
-    bool active = false, accepted = false;
-    double c2 = 0, mu = 0;
+    bool accepted = false;
     unsigned long long key = 0;
-    if (in_img) {
-        c2 = P.cov2[(size_t)y * P.state_pitch + x];
-        active = !(c2 < P.min_cov || c2 > P.max_cov);  // same gate as setup_kernel: the maps are untouched in between
-    }
-    double half = 0;
-    double2 pm = make_double2(0, 0), dir = make_double2(0, 0);
+    int x = 0, y = 0;
     if (active) {
-        // key, record and depth in one round trip (the accept rate of active pixels is > 90 %)
-        key = P.best[pidx];
-        const PixelRec *rec = P.rec + pidx;
-        pm = rec->pm; dir = rec->dir; half = rec->half;
-        mu = P.depth[(size_t)y * P.state_pitch + x];
+        key = P.best[slot];
+        const PixelRec *rec = P.rec + slot;
+        const double2 pm = rec->pm, dir = rec->dir;
+        const double half = rec->half;
+        const int4 xy = rec->xy;
+        const double2 mc = P.state_c[slot];
+        const double mu = mc.x, c2 = mc.y;
+        x = xy.x; y = xy.y;
         accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
+        if (accepted) {
+            const int k = key_index(key);
+            const double ex = dir.x, ey = dir.y;
+            const double l = sample_l(half, P.step, k);
+            const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
+            // updateDepthFilter ref:482-567
+            const D3 f_ref = unit_ray(P, (double)x, (double)y);
+            const D3 f_curr = unit_ray(P, cxp, cyp);
+            const D3 t{P.ti[0], P.ti[1], P.ti[2]};
+            const D3 f2 = qrot(P.qi, f_curr);
+            const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
+            const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
+            const double a10 = -a01;
+            // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
+            const double rdet = 1.0 / (a00 * a11 - a01 * a10);
+            const double ans0 = (b0 * a11 - a01 * b1) * rdet;
+            const double ans1 = (a00 * b1 - a10 * b0) * rdet;
+            const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
+                        0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
+            const double depth_est = sqrt(dot3(pe, pe));
+            // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
+            // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
+            // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
+            // transcendental call (|c| > 1 by rounding gives NaN on both routes).
+            const double t_norm = P.ti_norm;
+            const double rt = 1.0 / t_norm;
+            const double ca = dot3(f_ref, t) * rt;
+            const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
+            const double cb = -dot3(fcp, t) * rt;
+            const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
+            const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
+            const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
+            const double d_cov2 = d_cov * d_cov;
+            const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
+            const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
+            const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
+            const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
+            const double sig_fuse = (c2 * d_cov2) * rden;
+            P.depth[(size_t)y * P.state_pitch + x] = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
+            P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
+        }
+        if (P.write_flags) {
+            const size_t o = (size_t)y * P.flags_pitch + x;
+            P.flags[o] = (uint8_t)(1 | (accepted ? 2 : 0));
+            P.dbg_ncc[o] = (float)key_ncc(key);
+            const unsigned kb = key_has_winner(key) ? (unsigned)key_index(key) : 0xFFFFu;
+            const int trips = P.dbg_n[o] & 0xFFFF;
+            P.dbg_n[o] = (trips << 16) | (int)kb;
+        }
     }
-    if (accepted) {
-        const int k = key_index(key);
-        const double ex = dir.x, ey = dir.y;
-        const double l = sample_l(half, P.step, k);
-        const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
-        // updateDepthFilter ref:482-567
-        const D3 f_ref = unit_ray(P, (double)x, (double)y);
-        const D3 f_curr = unit_ray(P, cxp, cyp);
-        const D3 t{P.ti[0], P.ti[1], P.ti[2]};
-        const D3 f2 = qrot(P.qi, f_curr);
-        const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
-        const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
-        const double a10 = -a01;
-        // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
-        const double rdet = 1.0 / (a00 * a11 - a01 * a10);
-        const double ans0 = (b0 * a11 - a01 * b1) * rdet;
-        const double ans1 = (a00 * b1 - a10 * b0) * rdet;
-        const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
-                    0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
-        const double depth_est = sqrt(dot3(pe, pe));
-        // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
-        // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
-        // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
-        // transcendental call (|c| > 1 by rounding gives NaN on both routes).
-        const double t_norm = P.ti_norm;
-        const double rt = 1.0 / t_norm;
-        const double ca = dot3(f_ref, t) * rt;
-        const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
-        const double cb = -dot3(fcp, t) * rt;
-        const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
-        const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
-        const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
-        const double d_cov2 = d_cov * d_cov;
-        const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
-        const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
-        const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
-        const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
-        const double sig_fuse = (c2 * d_cov2) * rden;
-        P.depth[(size_t)y * P.state_pitch + x] = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
-        P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
-    }
-    if (P.write_flags && in_img) {
-        const size_t o = (size_t)y * P.flags_pitch + x;
-        P.flags[o] = (uint8_t)((active ? 1 : 0) | (accepted ? 2 : 0));
-        P.dbg_ncc[o] = active ? (float)key_ncc(key) : 0.0f;
-        const unsigned kb = key_has_winner(key) ? (unsigned)key_index(key) : 0xFFFFu;
-        const int trips = P.dbg_n[o] & 0xFFFF;
-        P.dbg_n[o] = active ? ((trips << 16) | (int)kb) : 0;
-    }
-    // counters: warp ballots -> shared -> ONE pair of global atomics per CTA (same-address atomics from
+    // accepted counter: warp ballots -> shared -> ONE global atomic per CTA (same-address atomics from
     // every warp serialise in L2 and were the critical path of this kernel)
-    __shared__ unsigned s_act, s_acc;
-    if (tid == 0) { s_act = 0; s_acc = 0; }
+    __shared__ unsigned s_acc;
+    if (tid == 0) s_acc = 0;
     __syncthreads();
-    const unsigned a = __popc(__ballot_sync(0xffffffffu, active));
     const unsigned c = __popc(__ballot_sync(0xffffffffu, accepted));
-    if (lane == 0) {
-        if (a) atomicAdd(&s_act, a);
-        if (c) atomicAdd(&s_acc, c);
-    }
+    if (lane == 0 && c) atomicAdd(&s_acc, c);
     __syncthreads();
-    if (tid == 0) {
-        if (s_act) atomicAdd(&P.counters[0], (unsigned long long)s_act);
-        if (s_acc) atomicAdd(&P.counters[2], (unsigned long long)s_acc);
-    }
+    if (tid == 0 && s_acc) atomicAdd(&P.counters[2], (unsigned long long)s_acc);
 }
 
 // ----------------------------------------------------------------------------------------
