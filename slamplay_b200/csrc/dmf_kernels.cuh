@@ -318,15 +318,14 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     const int n_full = n / CHUNK, tail = n % CHUNK;
     const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
     const int m_full = __reduce_max_sync(0xffffffffu, n_full);
-    unsigned my_rank = 0;
-#pragma unroll
-    for (int L = 1; L < CHUNK; ++L) {
-        const unsigned bal = __ballot_sync(0xffffffffu, tail == L);
-        if (lane == L) s_cnt[warp][L] = (unsigned)__popc(bal);
-        if (tail == L) my_rank = (unsigned)__popc(bal & lt_mask);
-    }
+    // lanes with the same tail length form a group (one MATCH instead of CHUNK-1 ballots): rank inside the group,
+    // and the group's first lane posts its size
+    const unsigned peers = __match_any_sync(0xffffffffu, tail);
+    const unsigned my_rank = (unsigned)__popc(peers & lt_mask);
     const unsigned act_bal = __ballot_sync(0xffffffffu, active);
-    if (lane == 0) { s_cnt[warp][CHUNK] = (unsigned)tot_full; s_cnt[warp][0] = (unsigned)__popc(act_bal); }
+    if (lane <= CHUNK) s_cnt[warp][lane] = (lane == 0) ? (unsigned)__popc(act_bal) : (lane == CHUNK) ? (unsigned)tot_full : 0u;
+    __syncwarp();
+    if (tail > 0 && my_rank == 0) s_cnt[warp][tail] = (unsigned)__popc(peers);
     __syncthreads();
     if (tid <= CHUNK) {
         unsigned pre[TILE_PIX / 32], tot = 0;
