@@ -47,7 +47,7 @@ struct dmf_ctx_impl {
     double2 *d_state_c = nullptr;              // per slot: (depth, cov2) as setup_kernel read them
     unsigned long long ctrl_idx = 0;
     int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
-    int2 *d_mom2 = nullptr;
+    dmf::mom2_t *d_mom2 = nullptr;
     uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
@@ -298,7 +298,7 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_ctrl, 2 * sizeof(dmf::Ctrl)));
         CUX(cudaMalloc(&c->d_state_c, np * sizeof(double2)));
         CUX(cudaMalloc(&c->d_mom1, W * H * sizeof(int4)));
-        CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(int2)));
+        CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(dmf::mom2_t)));
         CUX(cudaMalloc(&c->d_currx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_currx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));

@@ -95,6 +95,15 @@ struct __align__(16) PixelRec {
 };
 static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 
+#ifndef DMF_NCC_DSUM
+#define DMF_NCC_DSUM 1
+#endif
+#if DMF_NCC_DSUM
+typedef int mom2_t;   // the two diagonal Gram terms enter the NCC with the same weight: the table carries their sum
+#else
+typedef int2 mom2_t;
+#endif
+
 struct KParams {
     int width, height, border;
     // Rows owned by this context: local row rl in [0, n_rows) is image row
@@ -121,7 +130,7 @@ struct KParams {
     const uint2 *refx;    // expanded reference frame: refx[y*width + x] = bytes ref[y][x-3 .. x+3], 0   (ref_expand_kernel)
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
     const int4 *mom1;     // per block position of the current frame: {S, cQ, cH, cV}   (moments_kernel)
-    const int2 *mom2;     //                                          {cD1, cD2}
+    const mom2_t *mom2;   //                                          cD1 + cD2
     double *depth;
     double *cov2;
     // per-frame scratch, indexed by the slot of the active pixel (compacted by setup_kernel)
@@ -336,7 +345,9 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
         for (int w = 0; w < TILE_PIX / 32; ++w) s_base[w][tid] = base + pre[w];
     }
     __syncthreads();
-    // mark the 8-row groups of the moment table this CTA's samples read (moments_kernel skips the others)
+    // mark the 8-row groups of the moment table this CTA's samples read (moments_kernel skips the others).  One CTA-wide
+    // range with plain stores: per-warp marking (8x the same-address stores) and test-before-store (a dependent L2 round
+    // trip) were both measured slower for the whole kernel (+60 % / +17 %)
     if (s_need_hi >= s_need_lo)
         for (int g = (s_need_lo >> 3) + tid; g <= (s_need_hi >> 3); g += TILE_PIX) P.row_need[g] = 1;
     const unsigned slot = s_base[warp][0] + (unsigned)__popc(act_bal & lt_mask);
@@ -409,7 +420,7 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
 }
 
 __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
-                                                      int4 *__restrict__ mom1, int2 *__restrict__ mom2, int mom_pitch,
+                                                      int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
                                                       uint2 *__restrict__ currx, const uint8_t *__restrict__ row_need) {
     const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
     const int y0 = blockIdx.y * MOM_STRIP;
@@ -448,11 +459,13 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
         a.y = NCC_AREA * Q - S0 * S0;
         a.z = NCC_AREA * H - S0 * S1;
         a.w = NCC_AREA * V - S0 * S0n;
-        int2 b;
-        b.x = NCC_AREA * D1 - S0 * S1n;
-        b.y = NCC_AREA * D2 - S1 * S0n;
+        const int bx = NCC_AREA * D1 - S0 * S1n, by = NCC_AREA * D2 - S1 * S0n;
         mom1[(size_t)y * mom_pitch + x] = a;
-        mom2[(size_t)y * mom_pitch + x] = b;
+#if DMF_NCC_DSUM
+        mom2[(size_t)y * mom_pitch + x] = bx + by;  // |bx|, |by| < 2^30: exact
+#else
+        mom2[(size_t)y * mom_pitch + x] = make_int2(bx, by);
+#endif
         // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
         // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
         // funnel shifts (the 8x larger frame stays L2-resident: 16.6 MB at 1080p)
@@ -480,10 +493,40 @@ struct SampleInts {
     int cR00, cR10, cR01, cR11;                                                // 49*R - Sr*S per window
     int g0000, g1010, g0101, g1111, g0010, g0111, g0001, g1011, g0011, g1001;  // 49*G - S*S'
 };
+// 1/sqrt(a) for a normal, positive a: the approximation instruction (MUFU.RSQ64H) and one third-order correction —
+// the fast path of CUDA's rsqrt(), bit for bit, without its range check and slow-path call (a >= NCC_EPS_INT here).
+__device__ __forceinline__ double rsqrt_normal(double a) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    const double e = fma(a, -(y0 * y0), 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, y0 * e, y0);
+}
+
+#ifndef DMF_NCC_DSUM
+#define DMF_NCC_DSUM 1
+#endif
 // The FP64 part: combination with the bilinear weights of ref:169-172 (fractions fx, fy, ref:167-168);
-// den1 = 49*sum r^2 - (sum r)^2.  int -> double conversions run on the XU pipe (I2F.F64), idle otherwise.
+// den1 = 49*sum r^2 - (sum r)^2.  int -> double conversions run on the XU pipe (I2F.F64).
 __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, double fx, double fy) {
     const double gx = 1.0 - fx, gy = 1.0 - fy;
+#if DMF_NCC_DSUM
+    // w00 = gx*gy, w10 = fx*gy, w01 = gx*fy, w11 = fx*fy are separable, so
+    //   num  = gy (gx cR00 + fx cR10) + fy (gx cR01 + fx cR11)
+    //   den2 = w^T G w = gy^2 (gx^2 q00 + fx^2 q10 + 2 gx fx H0) + fy^2 (gx^2 q01 + fx^2 q11 + 2 gx fx H1)
+    //                    + 2 gy fy (gx^2 V0 + fx^2 V1 + gx fx (D1 + D2))
+    // with q = squares, H / V / D = horizontal / vertical / diagonal neighbour products of the centred Gram matrix;
+    // the two diagonal terms share one weight, so the table carries their (exact) integer sum.
+    double n0 = gx * (double)s.cR00; n0 = fma(fx, (double)s.cR10, n0);
+    double n1 = gx * (double)s.cR01; n1 = fma(fx, (double)s.cR11, n1);
+    const double num = fma(fy, n1, gy * n0);
+    const double A = gx * gx, B = gx * fx, C = fx * fx, D = gy * gy, E = gy * fy, F = fy * fy;
+    const double B2 = B + B, E2 = E + E;
+    double t0 = A * (double)s.g0000; t0 = fma(C, (double)s.g1010, t0); t0 = fma(B2, (double)s.g0010, t0);
+    double t1 = A * (double)s.g0101; t1 = fma(C, (double)s.g1111, t1); t1 = fma(B2, (double)s.g0111, t1);
+    double t2 = A * (double)s.g0001; t2 = fma(C, (double)s.g1011, t2); t2 = fma(B, (double)s.g0011, t2);
+    double den2 = D * t0; den2 = fma(F, t1, den2); den2 = fma(E2, t2, den2);
+#else
     const double w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
     double num = w00 * (double)s.cR00;
     num = fma(w10, (double)s.cR10, num);
@@ -499,8 +542,16 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
     double a2 = w00 * g0001; a2 = fma(w10, g1001, a2); a2 = fma(w01, g0101, a2); a2 = fma(w11, g0111, a2);
     double a3 = w00 * g0011; a3 = fma(w10, g1011, a3); a3 = fma(w01, g0111, a3); a3 = fma(w11, g1111, a3);
     double den2 = w00 * a0; den2 = fma(w10, a1, den2); den2 = fma(w01, a2, den2); den2 = fma(w11, a3, den2);
+#endif
     const double dd = fma(den1, den2, NCC_EPS_INT);
+#ifndef DMF_NCC_RSQRT
+#define DMF_NCC_RSQRT 0
+#endif
+#if DMF_NCC_RSQRT
+    return num * rsqrt_normal(dd);
+#else
     return num * rsqrt(dd);
+#endif
 }
 
 // K2b: NCC over the work units.
@@ -510,7 +561,11 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
 struct RawSample {
     uint32_t lo[8], hi[8];
     int4 m00, m10, m01, m11;
+#if DMF_NCC_DSUM
+    int md;   // cD1 + cD2
+#else
     int2 md;
+#endif
 };
 __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSample &r) {
     // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
@@ -530,8 +585,24 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
 __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
                                                  const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr) {
     int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
+#ifndef DMF_NCC_SHIFTBLK
+#define DMF_NCC_SHIFTBLK 0
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+#if DMF_NCC_SHIFTBLK
+        // windows a = 1 (block columns 1..7): the 64-bit block row shifted right by one byte meets the UNSHIFTED
+        // reference row (two SHF per row on the idle ALU pipe instead of 14 live registers of shifted reference rows)
+        const uint32_t lo1 = __funnelshift_r(r.lo[j], r.hi[j], 8), hi1 = r.hi[j] >> 8;
+        if (j > 0) {
+            R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
+            R11 = dp4(R0lo[j - 1], lo1, dp4(R0hi[j - 1], hi1, R11));
+        }
+        if (j < 7) {
+            R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
+            R10 = dp4(R0lo[j], lo1, dp4(R0hi[j], hi1, R10));
+        }
+#else
         if (j > 0) {
             R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
             R11 = dp4(R1lo[j - 1], r.lo[j], dp4(R1hi[j - 1], r.hi[j], R11));
@@ -540,6 +611,7 @@ __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint3
             R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
             R10 = dp4(R1lo[j], r.lo[j], dp4(R1hi[j], r.hi[j], R10));
         }
+#endif
     }
     SampleInts s;
     // exact centring in int32 (all terms < 2^31)
@@ -547,7 +619,11 @@ __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint3
     s.cR01 = NCC_AREA * R01 + nSr * r.m01.x; s.cR11 = NCC_AREA * R11 + nSr * r.m11.x;
     s.g0000 = r.m00.y; s.g1010 = r.m10.y; s.g0101 = r.m01.y; s.g1111 = r.m11.y;
     s.g0010 = r.m00.z; s.g0111 = r.m01.z; s.g0001 = r.m00.w; s.g1011 = r.m10.w;
+#if DMF_NCC_DSUM
+    s.g0011 = r.md; s.g1001 = 0;
+#else
     s.g0011 = r.md.x; s.g1001 = r.md.y;
+#endif
     return s;
 }
 // integer part and fraction of a sample coordinate c (0 <= c < 2^31), ref:167-168.  Adding 2^52 with round-down
@@ -638,8 +714,9 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             // position of the first sample; inside the loop the position of sample j+1 is computed
             // before the NCC of sample j so its FP64 chain is off the critical path
             double sx, sy;
+            double kd = int2double_fast(k0);  // sample index as a double: l_k = fma(step, k, -half) as in sample_l()
             {
-                const double l = sample_l(half, P.step, k0);
+                const double l = fma(P.step, kd, -half);
                 sx = fma(l, dir.x, pm.x);  // ref:433
                 sy = fma(l, dir.y, pm.y);
             }
@@ -647,7 +724,15 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             for (int j = 0; j < L; ++j) {
                 const double cx = sx, cy = sy;
                 {
-                    const double l = sample_l(half, P.step, k0 + j + 1);
+#ifndef DMF_NCC_KD
+#define DMF_NCC_KD 1
+#endif
+#if DMF_NCC_KD
+                    kd += 1.0;
+#else
+                    kd = int2double_fast(k0 + j + 1);
+#endif
+                    const double l = fma(P.step, kd, -half);
                     sx = fma(l, dir.x, pm.x);
                     sy = fma(l, dir.y, pm.y);
                 }
