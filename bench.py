@@ -53,14 +53,13 @@ def measured_peaks() -> dict:
 
 
 def ncc_traffic(workload: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one ncc_kernel launch from the committed ncu --set full
+    """dram__bytes_read.sum + dram__bytes_write.sum of one ncc_kernel launch (bytes) from the committed ncu --set full
     capture (profiles/r01_ncc_traffic.json): a mid-sequence launch of the 1080p workload; null for other workloads."""
     p = ROOT / "profiles" / "r01_ncc_traffic.json"
     try:
         j = json.loads(p.read_text())
         if j.get("workload") == workload:
-            return {"bytes_per_launch": j["dram_bytes_read"] + j["dram_bytes_write"], "unit": "B", "launch": "frame 40 of 299",
-                    "source": "profiles/r01_ncc_traffic.json"}
+            return j["dram_bytes_read"] + j["dram_bytes_write"]
     except Exception:
         pass
     return None
@@ -381,6 +380,7 @@ def ours(args) -> dict | None:
                 "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                 "frac": ncc_flops_launch / (ncc_launch_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS_NOMINAL,
                 "traffic": ncc_traffic(args.workload),
+                "traffic_note": "DRAM bytes of the ncc_kernel launch of frame 40 (profiles/r01_ncc_traffic.json); null where no capture exists",
                 "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1965 MHz); MEASURED_PEAKS.json has no FP32 figure",
                 "flop_model": "600 algorithmic FP32 flop per NCC evaluation (SURVEY.md 8d); the kernel itself computes the NCC from exact "
                               "integer moments (IDP.4A + a per-frame moment table) and is bound by L1/TEX gathers, see profiles/",

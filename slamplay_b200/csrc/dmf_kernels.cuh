@@ -32,11 +32,11 @@
 // exactly in int32 (49*R - Sr*S, 49*G - S*S').
 //   * S and the 10 centred Gram sums depend only on the current frame and the integer position
 //     of the block: moments_kernel computes them ONCE per frame for every block position
-//     (IDP.4A, 4 u8 MACs per instruction) into a 24 B/px table in HBM; a sample reads 5 vector
+//     (IDP.4A, 4 u8 MACs per instruction) into a 20 B/px table in HBM; a sample reads 5 vector
 //     loads from it instead of redoing ~136 dp4a.
 //   * the 4 cross sums need the reference patch: 56 IDP.4A per sample on manual __ldg gathers of
 //     the block (texture units filter with 8-bit weights and would break parity).
-//   * the final combination (bilinear weights, w^T G w, 1/sqrt) runs in FP64 on the otherwise
+//   * the final combination (bilinear weights, w^T G w in separable form, 1/sqrt) runs in FP64 on the otherwise
 //     idle FP64 pipe, so the NCC agrees with the reference's two-pass FP64 ZNCC to ~1e-13 and
 //     the arg-max / 0.85 decisions are the reference's except for exact ties.
 // Adjacent lanes hold adjacent pixels at the same chunk, so their gathers fall into the same
@@ -95,14 +95,7 @@ struct __align__(16) PixelRec {
 };
 static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 
-#ifndef DMF_NCC_DSUM
-#define DMF_NCC_DSUM 1
-#endif
-#if DMF_NCC_DSUM
 typedef int mom2_t;   // the two diagonal Gram terms enter the NCC with the same weight: the table carries their sum
-#else
-typedef int2 mom2_t;
-#endif
 
 struct KParams {
     int width, height, border;
@@ -386,12 +379,12 @@ __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)
 // Gram sums of the 8x8 block at each position (x,y) = top-left tap.  A sample whose top-left tap is
 // (bx,by) needs   mom1 at (bx,by),(bx+1,by),(bx,by+1),(bx+1,by+1)  and  mom2 at (bx,by):
 //   mom1(x,y) = { S(x,y), 49*Q - S^2, 49*H - S(x,y)S(x+1,y), 49*V - S(x,y)S(x,y+1) }   (Q,H,V: squares,
-//   mom2(x,y) = { 49*D1 - S(x,y)S(x+1,y+1), 49*D2 - S(x+1,y)S(x,y+1) }                  horizontal / vertical /
+//   mom2(x,y) = (49*D1 - S(x,y)S(x+1,y+1)) + (49*D2 - S(x+1,y)S(x,y+1))                 horizontal / vertical /
 //                                                                                        diagonal neighbour products)
 // A thread owns one column x and slides the 7-row window down a strip of MOM_STRIP rows: per step the
 // row (pair) leaving the window is subtracted and the row (pair) entering it is added, 28 IDP.4A per
 // position instead of 176 for a from-scratch 7x7 evaluation.  Adjacent threads hold adjacent columns,
-// so the row loads and the 24-byte table stores are coalesced.
+// so the row loads and the 20-byte table stores are coalesced.
 #ifndef DMF_MOM_STRIP
 #define DMF_MOM_STRIP 16
 #endif
@@ -461,11 +454,7 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
         a.w = NCC_AREA * V - S0 * S0n;
         const int bx = NCC_AREA * D1 - S0 * S1n, by = NCC_AREA * D2 - S1 * S0n;
         mom1[(size_t)y * mom_pitch + x] = a;
-#if DMF_NCC_DSUM
         mom2[(size_t)y * mom_pitch + x] = bx + by;  // |bx|, |by| < 2^30: exact
-#else
-        mom2[(size_t)y * mom_pitch + x] = make_int2(bx, by);
-#endif
         // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
         // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
         // funnel shifts (the 8x larger frame stays L2-resident: 16.6 MB at 1080p)
@@ -491,26 +480,12 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
 // (window a=1) of the SAME unshifted block words, so the block needs no per-sample byte shifts.
 struct SampleInts {
     int cR00, cR10, cR01, cR11;                                                // 49*R - Sr*S per window
-    int g0000, g1010, g0101, g1111, g0010, g0111, g0001, g1011, g0011, g1001;  // 49*G - S*S'
+    int g0000, g1010, g0101, g1111, g0010, g0111, g0001, g1011, gD;  // 49*G - S*S' (gD: the two diagonal terms summed)
 };
-// 1/sqrt(a) for a normal, positive a: the approximation instruction (MUFU.RSQ64H) and one third-order correction —
-// the fast path of CUDA's rsqrt(), bit for bit, without its range check and slow-path call (a >= NCC_EPS_INT here).
-__device__ __forceinline__ double rsqrt_normal(double a) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
-    const double e = fma(a, -(y0 * y0), 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    return fma(p, y0 * e, y0);
-}
-
-#ifndef DMF_NCC_DSUM
-#define DMF_NCC_DSUM 1
-#endif
 // The FP64 part: combination with the bilinear weights of ref:169-172 (fractions fx, fy, ref:167-168);
 // den1 = 49*sum r^2 - (sum r)^2.  int -> double conversions run on the XU pipe (I2F.F64).
 __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, double fx, double fy) {
     const double gx = 1.0 - fx, gy = 1.0 - fy;
-#if DMF_NCC_DSUM
     // w00 = gx*gy, w10 = fx*gy, w01 = gx*fy, w11 = fx*fy are separable, so
     //   num  = gy (gx cR00 + fx cR10) + fy (gx cR01 + fx cR11)
     //   den2 = w^T G w = gy^2 (gx^2 q00 + fx^2 q10 + 2 gx fx H0) + fy^2 (gx^2 q01 + fx^2 q11 + 2 gx fx H1)
@@ -524,34 +499,10 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
     const double B2 = B + B, E2 = E + E;
     double t0 = A * (double)s.g0000; t0 = fma(C, (double)s.g1010, t0); t0 = fma(B2, (double)s.g0010, t0);
     double t1 = A * (double)s.g0101; t1 = fma(C, (double)s.g1111, t1); t1 = fma(B2, (double)s.g0111, t1);
-    double t2 = A * (double)s.g0001; t2 = fma(C, (double)s.g1011, t2); t2 = fma(B, (double)s.g0011, t2);
+    double t2 = A * (double)s.g0001; t2 = fma(C, (double)s.g1011, t2); t2 = fma(B, (double)s.gD, t2);
     double den2 = D * t0; den2 = fma(F, t1, den2); den2 = fma(E2, t2, den2);
-#else
-    const double w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
-    double num = w00 * (double)s.cR00;
-    num = fma(w10, (double)s.cR10, num);
-    num = fma(w01, (double)s.cR01, num);
-    num = fma(w11, (double)s.cR11, num);
-    // den2 = w^T G w  with G the centred Gram matrix over the windows (00,10,01,11)
-    const double g0000 = (double)s.g0000, g1010 = (double)s.g1010, g0101 = (double)s.g0101, g1111 = (double)s.g1111;
-    const double g0010 = (double)s.g0010, g0111 = (double)s.g0111;
-    const double g0001 = (double)s.g0001, g1011 = (double)s.g1011;
-    const double g0011 = (double)s.g0011, g1001 = (double)s.g1001;
-    double a0 = w00 * g0000; a0 = fma(w10, g0010, a0); a0 = fma(w01, g0001, a0); a0 = fma(w11, g0011, a0);
-    double a1 = w00 * g0010; a1 = fma(w10, g1010, a1); a1 = fma(w01, g1001, a1); a1 = fma(w11, g1011, a1);
-    double a2 = w00 * g0001; a2 = fma(w10, g1001, a2); a2 = fma(w01, g0101, a2); a2 = fma(w11, g0111, a2);
-    double a3 = w00 * g0011; a3 = fma(w10, g1011, a3); a3 = fma(w01, g0111, a3); a3 = fma(w11, g1111, a3);
-    double den2 = w00 * a0; den2 = fma(w10, a1, den2); den2 = fma(w01, a2, den2); den2 = fma(w11, a3, den2);
-#endif
     const double dd = fma(den1, den2, NCC_EPS_INT);
-#ifndef DMF_NCC_RSQRT
-#define DMF_NCC_RSQRT 0
-#endif
-#if DMF_NCC_RSQRT
-    return num * rsqrt_normal(dd);
-#else
     return num * rsqrt(dd);
-#endif
 }
 
 // K2b: NCC over the work units.
@@ -561,11 +512,7 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
 struct RawSample {
     uint32_t lo[8], hi[8];
     int4 m00, m10, m01, m11;
-#if DMF_NCC_DSUM
     int md;   // cD1 + cD2
-#else
-    int2 md;
-#endif
 };
 __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSample &r) {
     // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
@@ -585,24 +532,8 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
 __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
                                                  const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr) {
     int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
-#ifndef DMF_NCC_SHIFTBLK
-#define DMF_NCC_SHIFTBLK 0
-#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#if DMF_NCC_SHIFTBLK
-        // windows a = 1 (block columns 1..7): the 64-bit block row shifted right by one byte meets the UNSHIFTED
-        // reference row (two SHF per row on the idle ALU pipe instead of 14 live registers of shifted reference rows)
-        const uint32_t lo1 = __funnelshift_r(r.lo[j], r.hi[j], 8), hi1 = r.hi[j] >> 8;
-        if (j > 0) {
-            R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
-            R11 = dp4(R0lo[j - 1], lo1, dp4(R0hi[j - 1], hi1, R11));
-        }
-        if (j < 7) {
-            R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
-            R10 = dp4(R0lo[j], lo1, dp4(R0hi[j], hi1, R10));
-        }
-#else
         if (j > 0) {
             R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
             R11 = dp4(R1lo[j - 1], r.lo[j], dp4(R1hi[j - 1], r.hi[j], R11));
@@ -611,7 +542,6 @@ __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint3
             R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
             R10 = dp4(R1lo[j], r.lo[j], dp4(R1hi[j], r.hi[j], R10));
         }
-#endif
     }
     SampleInts s;
     // exact centring in int32 (all terms < 2^31)
@@ -619,11 +549,7 @@ __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint3
     s.cR01 = NCC_AREA * R01 + nSr * r.m01.x; s.cR11 = NCC_AREA * R11 + nSr * r.m11.x;
     s.g0000 = r.m00.y; s.g1010 = r.m10.y; s.g0101 = r.m01.y; s.g1111 = r.m11.y;
     s.g0010 = r.m00.z; s.g0111 = r.m01.z; s.g0001 = r.m00.w; s.g1011 = r.m10.w;
-#if DMF_NCC_DSUM
-    s.g0011 = r.md; s.g1001 = 0;
-#else
-    s.g0011 = r.md.x; s.g1001 = r.md.y;
-#endif
+    s.gD = r.md;
     return s;
 }
 // integer part and fraction of a sample coordinate c (0 <= c < 2^31), ref:167-168.  Adding 2^52 with round-down
@@ -724,14 +650,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             for (int j = 0; j < L; ++j) {
                 const double cx = sx, cy = sy;
                 {
-#ifndef DMF_NCC_KD
-#define DMF_NCC_KD 1
-#endif
-#if DMF_NCC_KD
                     kd += 1.0;
-#else
-                    kd = int2double_fast(k0 + j + 1);
-#endif
                     const double l = fma(P.step, kd, -half);
                     sx = fma(l, dir.x, pm.x);
                     sy = fma(l, dir.y, pm.y);
