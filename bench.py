@@ -150,7 +150,7 @@ def render_frames_gpu(seq, torch, device):
 # the reference's CPU path (oracle port / compiled reference TU) on the host cores
 def default_cpu_rows(seq, target_ncc: float) -> int:
     """Rows of the CPU sample so that one pass costs about `target_ncc` NCC evaluations (the CPU path does
-    ~0.7 M NCC/s per core with the reference's heap allocations): ~20 NCC per pixel-update on these sequences."""
+    ~1.9 M NCC/s per core with the reference's heap allocations on the GPU box's host): ~20 NCC per pixel-update on these sequences."""
     p = seq.params
     per_row = (p.width - 2 * p.border) * 20.0 * (seq.n_frames - 1)
     return max(1, int(round(target_ncc / per_row)))
@@ -220,7 +220,7 @@ def reference_arm(args) -> dict:
         rows, stride = list(range(p.border, h - p.border)), 1
         sample = f"full {w}x{h} sequence, {seq.n_frames - 1} updates, compiled reference TU (oracle/_ref)"
     else:
-        rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 6e6 * cores))  # ~10 s per step
+        rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 1.2e7 * cores))  # ~7 s per step
         sample = (f"{len(rows)} of {h - 2 * p.border} interior rows (every {stride}th from y={rows[0]}) x all "
                   f"{seq.n_frames - 1} updates of {args.workload}; oracle port with the reference's per-NCC heap allocations")
     spec = (rows[0], stride, len(rows))
@@ -509,7 +509,7 @@ def cpu_baseline_and_parity(args, seq, frames, sf, torch) -> dict:
     p = seq.params
     h, w = seq.shape
     cores = os.cpu_count() or 1
-    rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 1.2e7 * cores))  # ~20 s
+    rows, stride = cpu_rows_sample(p, args.cpu_rows or default_cpu_rows(seq, 3.6e7 * cores))  # ~15-20 s (measured: ~1.9 M NCC/s per host core)
     host_frames = frames[:, :, :w].cpu().numpy()
     spec = (rows[0], stride, len(rows))
     dt, cnts, d_ref, c_ref = run_cpu_sequence(seq, host_frames, spec, heap=True, use_ref_tu=False, threads=cores)
