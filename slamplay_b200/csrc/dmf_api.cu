@@ -51,6 +51,7 @@ struct dmf_ctx_impl {
     uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
+    void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
     // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
     bool timing_on = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -155,7 +156,7 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_currx, c->d_row_need);
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
-        dmf::ncc_kernel<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
+        c->ncc_fn<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
         dmf::fuse_kernel<<<(c->n_pix + dmf::TILE_PIX - 1) / dmf::TILE_PIX, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
@@ -305,7 +306,14 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMemsetAsync(c->d_ctrl, 0, 2 * sizeof(dmf::Ctrl), c->stream));
         int per_sm = 0;
-        CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmf::ncc_kernel, dmf::NCC_THREADS, 0));
+        switch (params->width) {  // compile-time widths: the row loads of a sample become immediate offsets
+            case 640: c->ncc_fn = dmf::ncc_kernel<640>; break;
+            case 1241: c->ncc_fn = dmf::ncc_kernel<1241>; break;
+            case 1920: c->ncc_fn = dmf::ncc_kernel<1920>; break;
+            case 3840: c->ncc_fn = dmf::ncc_kernel<3840>; break;
+            default: c->ncc_fn = dmf::ncc_kernel<0>; break;
+        }
+        CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ncc_fn, dmf::NCC_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         c->ncc_grid = prop.multiProcessorCount * per_sm;  // persistent CTAs: one resident wave
     }

@@ -514,18 +514,22 @@ struct RawSample {
     int4 m00, m10, m01, m11;
     int md;   // cD1 + cD2
 };
+// WIDTH: image width as a compile-time constant (0 = use P.width).  With a constant width the eight row loads share
+// one base address and differ by immediate offsets (no per-row address arithmetic, no row-pointer registers).
+template <int WIDTH>
 __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSample &r) {
+    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
     // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
-    const unsigned o = (unsigned)(iy - 3) * (unsigned)P.width + (unsigned)(ix - 3);
+    const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
     const uint2 *xp = P.currx + o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint2 q = __ldg(xp + (size_t)j * (unsigned)P.width);
+        const uint2 q = __ldg(xp + (size_t)j * W);
         r.lo[j] = q.x; r.hi[j] = q.y;
     }
     const int4 *m1 = P.mom1 + o;
     r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1);
-    r.m01 = __ldg(m1 + (unsigned)P.width); r.m11 = __ldg(m1 + (unsigned)P.width + 1);
+    r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1);
     r.md = __ldg(P.mom2 + o);
 }
 // cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring
@@ -583,6 +587,7 @@ __device__ __forceinline__ void fetch_units(const KParams &P, const unsigned (&c
     }
 }
 
+template <int WIDTH>
 __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
     const int lane = threadIdx.x & 31;
     // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
@@ -624,10 +629,11 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             // reference patch of (x,y) into registers: 7 aligned 64-bit words of the expanded reference frame
             uint32_t R0lo[7], R0hi[7], R1lo[7], R1hi[7];
             {
-                const uint2 *rp = P.refx + (unsigned)(y - 3) * (unsigned)P.width + (unsigned)x;
+                const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
+                const uint2 *rp = P.refx + (unsigned)(y - 3) * W + (unsigned)x;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) {
-                    const uint2 q = __ldg(rp + (size_t)j * (unsigned)P.width);
+                    const uint2 q = __ldg(rp + (size_t)j * W);
                     R0lo[j] = q.x; R0hi[j] = q.y;
                     R1lo[j] = q.x << 8; R1hi[j] = __funnelshift_l(q.x, q.y, 8);
                 }
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 split_coord(cy, iy, fy);
                 if (ix != hix || iy != hiy) {
                     RawSample raw;
-                    load_raw(P, ix, iy, raw);
+                    load_raw<WIDTH>(P, ix, iy, raw);
                     si = reduce_raw(raw, R0lo, R0hi, R1lo, R1hi, nSr);
                     hix = ix; hiy = iy;
                 }
