@@ -49,7 +49,7 @@ typedef enum dmf_status {
 typedef struct dmf_params {
     int32_t width;          /* :73  */
     int32_t height;         /* :74  */
-    int32_t border;         /* :72  (20) */
+    int32_t border;         /* :72  (20); >= 13 */
     int32_t ncc_half;       /* :79  ncc_window_size (3); only 3 is supported by the kernels */
     double fx, fy, cx, cy;  /* :75-78 (float literals widened to double) */
     double step;            /* :432 0.7 */
@@ -142,8 +142,12 @@ int dmf_download_state(dmf_ctx *ctx, double *depth, size_t depth_step,
  * device staging buffer) before return unless it is pinned memory obtained from
  * dmf_alloc_pinned(), in which case it must stay untouched until dmf_sync().
  * _device: frame already in HBM on ctx's device (e.g. received by NCCL broadcast);
- * the launch is ordered after everything previously enqueued on `wait_stream`
- * (a cudaStream_t, may be NULL).
+ * the kernels that read it are ordered after everything previously enqueued on
+ * `wait_stream` (a cudaStream_t).  With wait_stream == NULL the frame must be
+ * complete in device memory when the call is made: the frame-only precompute runs
+ * on an internal stream beside the previous update and is NOT ordered after work
+ * enqueued on the context stream.  The frame must stay untouched until an event
+ * recorded on the context stream after this call has completed (or dmf_sync()).
  */
 int dmf_update(dmf_ctx *ctx, const uint8_t *curr_host, size_t step,
                const double q_xyzw[4], const double t_xyz[3]);

@@ -22,8 +22,8 @@ struct dmf_ctx_impl {
     int row0 = 0, blk = 1, cyc = 1, ph = 0, n_rows = 0;
     std::vector<std::pair<int, int>> spans;     // owned interior rows as ascending [y0, y1) intervals
     std::vector<std::pair<int, int>> io_spans;  // rows moved by upload / download (spans, plus border rows a contiguous band asked for)
-    uint8_t *d_row_need = nullptr;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // stream: setup -> ncc -> fuse of every frame; mom_stream: moments_kernel of the NEXT frame runs beside them
+    cudaStream_t stream = nullptr, copy_stream = nullptr, mom_stream = nullptr;
     // images
     uint8_t *d_ref = nullptr;
     uint8_t *d_curr[2] = {nullptr, nullptr};
@@ -46,9 +46,13 @@ struct dmf_ctx_impl {
     dmf::Ctrl *d_ctrl = nullptr;               // two control blocks: frame k uses [k & 1], fuse_kernel re-arms the other
     double2 *d_state_c = nullptr;              // per slot: (depth, cov2) as setup_kernel read them
     unsigned long long ctrl_idx = 0;
-    int4 *d_mom1 = nullptr;                    // per-frame block-moment table (moments_kernel)
-    dmf::mom2_t *d_mom2 = nullptr;
-    uint2 *d_currx = nullptr;                  // expanded current frame (written by moments_kernel)
+    // per-frame block-moment table + expanded current frame (moments_kernel), double-buffered by frame parity
+    int4 *d_mom1[2] = {nullptr, nullptr};
+    dmf::mom2_t *d_mom2[2] = {nullptr, nullptr};
+    uint2 *d_currx[2] = {nullptr, nullptr};
+    cudaEvent_t ev_mom_done[2] = {nullptr, nullptr};  // moments_kernel wrote table b (mom_stream)
+    cudaEvent_t ev_tab_free[2] = {nullptr, nullptr};  // ncc_kernel that read table b finished (stream)
+    cudaEvent_t ev_frame = nullptr;                   // the frame of this update is complete in HBM
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
@@ -100,7 +104,7 @@ int check_params(const dmf_params *p, std::string &why) {
     if (!p) { why = "params is NULL"; return -1; }
     if (p->width < 64 || p->height < 64 || p->width > 32768 || p->height > 32768) { why = "width/height out of range [64,32768]"; return -1; }
     if (p->ncc_half != 3) { why = "only ncc_half == 3 (7x7 window, ref:79) is supported"; return -1; }
-    if (p->border < 4 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 4 and < min(width,height)/2"; return -1; }
+    if (p->border < 13 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 13 (the moment table covers block positions x <= width-16, y <= height-9) and < min(width,height)/2"; return -1; }
     // the arg-max key holds sample indices < 510 (KEY_IDX_BITS = 9); the work-unit encoding chunk indices < 64
     if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 250.0)) { why = "step must be > 0 and max_half_len/step <= 250"; return -1; }
     if ((long long)(p->width - 2 * p->border) * (p->height - 2 * p->border) >= (1ll << 26)) { why = "more than 2^26 interior pixels"; return -1; }
@@ -109,12 +113,14 @@ int check_params(const dmf_params *p, std::string &why) {
     return 0;
 }
 
-int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3]) {
+// frame_ready: event after which the frame at d_curr is complete (NULL: it already is when this call is made).
+int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3],
+                  cudaEvent_t frame_ready, cudaEvent_t frame_consumed) {
     dmf::KParams K{};
     const dmf_params &p = c->prm;
+    const int b = (int)(c->ctrl_idx & 1);  // parity of this update: control block and moment-table buffer
     K.width = p.width; K.height = p.height; K.border = p.border;
     K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows;
-    K.row_need = c->d_row_need;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
     K.ncc_thresh = p.ncc_thresh;
     K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
@@ -133,9 +139,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.wi = p.width - 2 * p.border;
     K.n_pix = c->n_pix;
     K.rec = c->d_rec;
-    K.mom1 = c->d_mom1; K.mom2 = c->d_mom2; K.mom_pitch = p.width; K.currx = c->d_currx;
+    K.mom1 = c->d_mom1[b]; K.mom2 = c->d_mom2[b]; K.mom_pitch = p.width; K.currx = c->d_currx[b];
     K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.state_c = c->d_state_c;
-    K.ctrl = c->d_ctrl + (c->ctrl_idx & 1); K.ctrl_next = c->d_ctrl + ((c->ctrl_idx + 1) & 1);
+    K.ctrl = c->d_ctrl + b; K.ctrl_next = c->d_ctrl + (b ^ 1);
     const int rows = c->n_rows;
     if (rows > 0) {
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
@@ -150,18 +156,32 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
                 }
                 ev[i] = c->ev_pool[c->ev_used++];
             }
-            CU(cudaEventRecord(ev[0], c->stream));
         }
+        // moments_kernel needs only the frame, not the state: it runs on its own stream, beside setup / ncc / fuse of
+        // the PREVIOUS update (whose ncc_kernel reads the other table buffer).  With per-kernel timing on, everything
+        // is serialised on the context stream so that the event pairs bracket one kernel each.
+        cudaStream_t ms = c->timing_on ? c->stream : c->mom_stream;
+        if (frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));
+        if (ms != c->stream) CU(cudaStreamWaitEvent(ms, c->ev_tab_free[b], 0));  // ncc_kernel of two updates ago
+        if (ev[0]) CU(cudaEventRecord(ev[0], c->stream));
         dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
-        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, c->stream>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1, c->d_mom2, p.width, c->d_currx, c->d_row_need);
+        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
+        if (frame_consumed) CU(cudaEventRecord(frame_consumed, ms));
+        if (ms != c->stream) {
+            CU(cudaEventRecord(c->ev_mom_done[b], ms));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_mom_done[b], 0));
+        }
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         c->ncc_fn<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
+        CU(cudaEventRecord(c->ev_tab_free[b], c->stream));
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
         dmf::fuse_kernel<<<(c->n_pix + dmf::TILE_PIX - 1) / dmf::TILE_PIX, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
         CU(cudaGetLastError());
         c->ctrl_idx++;
+    } else if (frame_consumed) {
+        CU(cudaEventRecord(frame_consumed, c->stream));
     }
     c->frames++;
     return DMF_OK;
@@ -264,6 +284,8 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
     } while (0)
     CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUX(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUX(cudaStreamCreateWithFlags(&c->mom_stream, cudaStreamNonBlocking));
+    CUX(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
     const size_t img_bytes = (size_t)c->img_pitch * H;
     CUX(cudaMalloc(&c->d_ref, img_bytes));
     for (int b = 0; b < 2; ++b) {
@@ -277,8 +299,6 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
     CUX(cudaMalloc(&c->d_depth, W * H * sizeof(double)));
     CUX(cudaMalloc(&c->d_cov2, W * H * sizeof(double)));
     CUX(cudaMalloc(&c->d_flags, W * H));
-    CUX(cudaMalloc(&c->d_row_need, H));
-    CUX(cudaMemsetAsync(c->d_row_need, 0, H, c->stream));
     CUX(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
     CUX(cudaMalloc(&c->d_eval, sizeof(double)));
     CUX(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
@@ -298,10 +318,16 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_ctrl, 2 * sizeof(dmf::Ctrl)));
         CUX(cudaMalloc(&c->d_state_c, np * sizeof(double2)));
-        CUX(cudaMalloc(&c->d_mom1, W * H * sizeof(int4)));
-        CUX(cudaMalloc(&c->d_mom2, W * H * sizeof(dmf::mom2_t)));
-        CUX(cudaMalloc(&c->d_currx, W * H * sizeof(uint2)));
-        CUX(cudaMemsetAsync(c->d_currx, 0, W * H * sizeof(uint2), c->stream));
+        for (int b = 0; b < 2; ++b) {
+            CUX(cudaMalloc(&c->d_mom1[b], W * H * sizeof(int4)));
+            CUX(cudaMalloc(&c->d_mom2[b], W * H * sizeof(dmf::mom2_t)));
+            CUX(cudaMalloc(&c->d_currx[b], W * H * sizeof(uint2)));
+            CUX(cudaMemsetAsync(c->d_mom1[b], 0, W * H * sizeof(int4), c->stream));
+            CUX(cudaMemsetAsync(c->d_mom2[b], 0, W * H * sizeof(dmf::mom2_t), c->stream));
+            CUX(cudaMemsetAsync(c->d_currx[b], 0, W * H * sizeof(uint2), c->stream));
+            CUX(cudaEventCreateWithFlags(&c->ev_mom_done[b], cudaEventDisableTiming));
+            CUX(cudaEventCreateWithFlags(&c->ev_tab_free[b], cudaEventDisableTiming));
+        }
         CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
         CUX(cudaMemsetAsync(c->d_ctrl, 0, 2 * sizeof(dmf::Ctrl), c->stream));
@@ -346,6 +372,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->mom_stream) cudaStreamSynchronize(ctx->mom_stream);
     cudaFree(ctx->d_ref);
     for (int b = 0; b < 2; ++b) {
         cudaFree(ctx->d_curr[b]);
@@ -357,11 +384,17 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_state_c); cudaFree(ctx->d_mom1); cudaFree(ctx->d_mom2); cudaFree(ctx->d_currx); cudaFree(ctx->d_refx);
-    cudaFree(ctx->d_row_need);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_state_c); cudaFree(ctx->d_refx);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->d_mom1[b]); cudaFree(ctx->d_mom2[b]); cudaFree(ctx->d_currx[b]);
+        if (ctx->ev_mom_done[b]) cudaEventDestroy(ctx->ev_mom_done[b]);
+        if (ctx->ev_tab_free[b]) cudaEventDestroy(ctx->ev_tab_free[b]);
+    }
+    if (ctx->ev_frame) cudaEventDestroy(ctx->ev_frame);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->mom_stream) cudaStreamDestroy(ctx->mom_stream);
     delete ctx;
 }
 
@@ -470,11 +503,7 @@ int dmf_update(dmf_ctx *c, const uint8_t *curr_host, size_t step, const double q
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
     CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, src, src_step, W, H, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    int rc = launch_update(c, c->d_curr[b], c->img_pitch, q, t);
-    if (rc) return rc;
-    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
-    return DMF_OK;
+    return launch_update(c, c->d_curr[b], c->img_pitch, q, t, c->ev_copied[b], c->ev_consumed[b]);
 }
 
 int dmf_update_device(dmf_ctx *c, const uint8_t *curr_dev, size_t step, const double q[4], const double t[3], void *wait_stream) {
@@ -482,27 +511,28 @@ int dmf_update_device(dmf_ctx *c, const uint8_t *curr_dev, size_t step, const do
     if (!c->have_ref) return fail(c, DMF_ERR_STATE, "dmf_update_device: dmf_set_reference() has not been called");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_update_device: step < width");
     CU(cudaSetDevice(c->device));
+    cudaEvent_t ready = nullptr;
     if (wait_stream) {
         CU(cudaEventRecord(c->ev_ext, (cudaStream_t)wait_stream));
-        CU(cudaStreamWaitEvent(c->stream, c->ev_ext, 0));
+        ready = c->ev_ext;
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(curr_dev) & 3u) == 0) && (step % 4 == 0) && step <= 0x7fffffff;
-    if (aligned) return launch_update(c, curr_dev, (int)step, q, t);
-    // unaligned device frame: repack into an internal pitched buffer on the compute stream
+    if (aligned) return launch_update(c, curr_dev, (int)step, q, t, ready, nullptr);
+    // unaligned device frame: repack into an internal pitched buffer on the copy stream
     const int b = (int)(c->frame_idx & 1);
     c->frame_idx++;
-    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-    CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, curr_dev, step, c->prm.width, c->prm.height, cudaMemcpyDeviceToDevice, c->stream));
-    int rc = launch_update(c, c->d_curr[b], c->img_pitch, q, t);
-    if (rc) return rc;
-    CU(cudaEventRecord(c->ev_consumed[b], c->stream));
-    return DMF_OK;
+    if (ready) CU(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, curr_dev, step, c->prm.width, c->prm.height, cudaMemcpyDeviceToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    return launch_update(c, c->d_curr[b], c->img_pitch, q, t, c->ev_copied[b], c->ev_consumed[b]);
 }
 
 int dmf_sync(dmf_ctx *c) {
     if (!c) return fail(c, DMF_ERR_INVALID, "dmf_sync: NULL context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->mom_stream));
     CU(cudaStreamSynchronize(c->stream));
     return DMF_OK;
 }

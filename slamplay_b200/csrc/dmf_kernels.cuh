@@ -134,7 +134,6 @@ struct KParams {
     unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
     Ctrl *ctrl;                                    // this frame's control block
     Ctrl *ctrl_next;                               // the next frame's (re-armed by fuse_kernel)
-    uint8_t *row_need;                             // [height/8 + 1]: 8-row groups of the moment table some sample reads
     uint8_t *flags;
     float *dbg_ncc;  // with write_flags: best NCC per active pixel (rounded to f32)
     int *dbg_n;      // with write_flags: (trip count << 16) | winning iteration (0xFFFF: none)
@@ -272,7 +271,6 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
 
     int n = 0;
     bool active = false;
-    int need_lo = 0x7fffffff, need_hi = -1;  // moment-table rows this pixel's samples read
     double mu = 0, c2 = 0, pmx = 0, pmy = 0, lx = 0, ly = 0, half = 0;
     int2 st = make_int2(0, 0);
     if (in_img) {
@@ -287,13 +285,6 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
                 while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
                 while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
             }
-            if (n > 0) {
-                // sample rows span pmy -/+ half*ly; a sample with integer row iy reads table rows iy-3, iy-2
-                const double ya = fma(-half, ly, pmy), yb = fma(half, ly, pmy);
-                const double ylo = fmin(ya, yb), yhi = fmax(ya, yb);
-                need_lo = max((int)fmax(ylo, (double)P.border) - 3, 0);
-                need_hi = min((int)fmin(yhi, (double)(P.height - P.border)) - 2 + 6, P.height - 1);  // +6: block rows iy-3..iy+4 of the expanded frame
-            }
             st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
         }
         if (P.write_flags) {  // debug planes: fuse_kernel only visits active pixels
@@ -306,16 +297,9 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     // ---- slots and work units.  Space is claimed once per CTA and per list (thread L does the atomicAdd for list L,
     // thread 0 the one for the active-pixel slots, so the latency is paid once per CTA instead of by every warp);
     // every warp then writes its units chunk-major so that adjacent list entries hold adjacent pixels of one image row.
-    __shared__ int s_need_lo, s_need_hi;                   // moment-table rows the CTA's samples read
     __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
     __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first entry of that warp in list L / first slot
     const int warp = tid >> 5;
-    if (tid == 0) { s_need_lo = 0x7fffffff; s_need_hi = -1; }
-    __syncthreads();
-    {
-        const int lo = __reduce_min_sync(0xffffffffu, need_lo), hi = __reduce_max_sync(0xffffffffu, need_hi);
-        if (lane == 0 && hi >= lo) { atomicMin(&s_need_lo, lo); atomicMax(&s_need_hi, hi); }
-    }
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_full = n / CHUNK, tail = n % CHUNK;
     const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
@@ -338,11 +322,6 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
         for (int w = 0; w < TILE_PIX / 32; ++w) s_base[w][tid] = base + pre[w];
     }
     __syncthreads();
-    // mark the 8-row groups of the moment table this CTA's samples read (moments_kernel skips the others).  One CTA-wide
-    // range with plain stores: per-warp marking (8x the same-address stores) and test-before-store (a dependent L2 round
-    // trip) were both measured slower for the whole kernel (+60 % / +17 %)
-    if (s_need_hi >= s_need_lo)
-        for (int g = (s_need_lo >> 3) + tid; g <= (s_need_hi >> 3); g += TILE_PIX) P.row_need[g] = 1;
     const unsigned slot = s_base[warp][0] + (unsigned)__popc(act_bal & lt_mask);
     if (active) {
         PixelRec *rec = P.rec + slot;  // four 16-byte vector stores
@@ -414,14 +393,11 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
 
 __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                       int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                      uint2 *__restrict__ currx, const uint8_t *__restrict__ row_need) {
+                                                      uint2 *__restrict__ currx) {
     const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
     const int y0 = blockIdx.y * MOM_STRIP;
     const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
-    // skip strips none of whose 8-row groups is read by a sample of this frame (CTA-uniform)
-    bool need = false;
-    for (int g = y0 >> 3; g <= (min(y0 + MOM_STRIP, height) - 1) >> 3; ++g) need |= (row_need[g] != 0);
-    if (!need || x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
+    if (x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
 
     const uint8_t *base = img + (size_t)y0 * pitch + x;
     const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
@@ -698,7 +674,6 @@ __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(con
     const unsigned n_active = P.ctrl->count[0];
     if (blockIdx.x == 0) {
         if (tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) reinterpret_cast<unsigned *>(P.ctrl_next)[tid] = 0;
-        for (int r = tid; r < P.height / 8 + 1; r += TILE_PIX) P.row_need[r] = 0;  // ncc_kernel / moments_kernel of this frame are done
         if (tid == 0 && n_active) atomicAdd(&P.counters[0], (unsigned long long)n_active);
     }
     const unsigned slot = blockIdx.x * TILE_PIX + tid;
