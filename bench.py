@@ -303,7 +303,10 @@ def ours(args) -> dict | None:
         poses = sf.broadcast_poses(poses_all if rank == 0 else None) if world > 1 else [(T.q, T.t) for T in poses_all]
         for i in range(1, F):
             sf.update(frames[i] if rank == 0 else None, poses[i])
-        return sf.gather_state() if world > 1 else None
+        if world > 1:
+            return sf.gather_state()
+        sf.flush()  # the deferred fusion of the last update belongs to this step
+        return None
 
     # ---- device-timed value ---------------------------------------------------------------
     for _ in range(args.warmup):
@@ -395,7 +398,9 @@ def ours(args) -> dict | None:
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"},
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (4 * n_upd + 1),  # setup, moments, ncc, fuse per update + the state fill
+            # per step: state fill, setup_kernel of the first update, advance_kernel of the others (fusion of the
+            # previous update + setup), moments_kernel and ncc_kernel per update, fuse_kernel of the last update
+            "gpu_launches": args.steps * (3 * n_upd + 2),
         }
 
     # ---- end-to-end through the public API with HOST buffers ---------------------------------

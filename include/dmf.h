@@ -154,6 +154,14 @@ int dmf_update(dmf_ctx *ctx, const uint8_t *curr_host, size_t step,
 int dmf_update_device(dmf_ctx *ctx, const uint8_t *curr_dev, size_t step,
                       const double q_xyzw[4], const double t_xyz[3], void *wait_stream);
 
+/*
+ * The Gaussian fusion (:546-564) of an update is deferred: it runs inside the next
+ * update's first kernel (its result feeds the next search straight from registers),
+ * or as soon as anything reads or replaces the maps (every accessor below does so
+ * implicitly).  dmf_flush() enqueues a pending fusion on the context stream without
+ * waiting for it; dmf_sync() does the same and waits for all streams of the context.
+ */
+int dmf_flush(dmf_ctx *ctx);
 int dmf_sync(dmf_ctx *ctx);
 
 /*

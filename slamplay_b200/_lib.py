@@ -70,6 +70,7 @@ DMF_SYMBOLS = {
     "dmf_download_state": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
     "dmf_update": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double)]),
     "dmf_update_device": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double), _vp]),
+    "dmf_flush": (C.c_int, [_vp]),
     "dmf_sync": (C.c_int, [_vp]),
     "dmf_set_timing": (C.c_int, [_vp, C.c_int]),
     "dmf_get_timing": (C.c_int, [_vp, _P(C.c_double), _P(C.c_uint64), C.c_int]),

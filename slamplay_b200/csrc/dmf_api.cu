@@ -40,12 +40,19 @@ struct dmf_ctx_impl {
     unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
     double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
     // per-frame scratch of the three-kernel update (setup -> ncc -> fuse)
-    dmf::PixelRec *d_rec = nullptr;            // n_pix 64-byte records
-    unsigned long long *d_best = nullptr;
+    // slot-indexed scratch, double-buffered by update parity (advance_kernel reads update k's while writing k+1's)
+    dmf::PixelRec *d_rec[2] = {nullptr, nullptr};            // n_pix 64-byte records
+    unsigned long long *d_best[2] = {nullptr, nullptr};
     unsigned int *d_units_full = nullptr, *d_units_tail = nullptr;
-    dmf::Ctrl *d_ctrl = nullptr;               // two control blocks: frame k uses [k & 1], fuse_kernel re-arms the other
-    double2 *d_state_c = nullptr;              // per slot: (depth, cov2) as setup_kernel read them
-    unsigned long long ctrl_idx = 0;
+    dmf::Ctrl *d_ctrl = nullptr;               // three control blocks: update u uses [u % 3]; the kernel that finishes update f re-arms [(f + 2) % 3]
+    double2 *d_state_c[2] = {nullptr, nullptr};  // per slot: (depth, cov2) the update started from
+    unsigned long long seq = 0;                // index of the next update
+    unsigned int *d_cta_cnt = nullptr;         // two arrays (update parity) of per-CTA active-pixel counts
+    int tiles_x = 0, n_bands = 0, n_ctas = 0, n_slots = 0;
+    // Lazy fusion: the fusion of the last update runs inside the NEXT update's advance_kernel, or in fuse_kernel as
+    // soon as anything reads or replaces the maps (flush_pending).
+    bool pending = false;
+    double pend_qi[4] = {0, 0, 0, 1}, pend_ti[3] = {0, 0, 0}, pend_ti_norm = 0;
     // per-frame block-moment table + expanded current frame (moments_kernel), double-buffered by frame parity
     int4 *d_mom1[2] = {nullptr, nullptr};
     dmf::mom2_t *d_mom2[2] = {nullptr, nullptr};
@@ -113,12 +120,9 @@ int check_params(const dmf_params *p, std::string &why) {
     return 0;
 }
 
-// frame_ready: event after which the frame at d_curr is complete (NULL: it already is when this call is made).
-int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3],
-                  cudaEvent_t frame_ready, cudaEvent_t frame_consumed) {
-    dmf::KParams K{};
+void fill_kparams(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long u) {
     const dmf_params &p = c->prm;
-    const int b = (int)(c->ctrl_idx & 1);  // parity of this update: control block and moment-table buffer
+    const int b = (int)(u & 1);  // parity of update u: slot buffers and moment-table buffer
     K.width = p.width; K.height = p.height; K.border = p.border;
     K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
@@ -126,24 +130,62 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
     K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
     K.step = p.step; K.max_half_len = p.max_half_len; K.min_depth = p.min_depth; K.n_sigma = p.n_sigma;
     K.min_cov = p.min_cov; K.max_cov = p.max_cov;
-    for (int i = 0; i < 4; ++i) K.q[i] = q[i];
-    for (int i = 0; i < 3; ++i) K.t[i] = t[i];
-    se3_inverse(q, t, K.qi, K.ti);
-    K.ti_norm = std::sqrt(K.ti[0] * K.ti[0] + (K.ti[1] * K.ti[1] + K.ti[2] * K.ti[2]));
     K.bd = (double)p.border; K.wd = (double)p.width; K.hd = (double)p.height;
     K.inv_fx = 1.0 / p.fx; K.inv_fy = 1.0 / p.fy; K.inv_step = 1.0 / p.step;
-    K.curr = d_curr; K.ref = c->d_ref; K.refx = c->d_refx; K.refstat = c->d_refstat;
+    K.ref = c->d_ref; K.refx = c->d_refx; K.refstat = c->d_refstat;
     K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
-    K.curr_pitch = curr_pitch; K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
+    K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
     K.flags_pitch = p.width;
     K.wi = p.width - 2 * p.border;
     K.n_pix = c->n_pix;
-    K.rec = c->d_rec;
     K.mom1 = c->d_mom1[b]; K.mom2 = c->d_mom2[b]; K.mom_pitch = p.width; K.currx = c->d_currx[b];
-    K.best = c->d_best; K.units_full = c->d_units_full; K.units_tail = c->d_units_tail; K.state_c = c->d_state_c;
-    K.ctrl = c->d_ctrl + b; K.ctrl_next = c->d_ctrl + (b ^ 1);
+    K.units_full = c->d_units_full; K.units_tail = c->d_units_tail;
+    K.rec = c->d_rec[b]; K.state_c = c->d_state_c[b]; K.best = c->d_best[b];
+    K.ctrl = c->d_ctrl + (u % 3);
+    K.cta_cnt = c->d_cta_cnt + (size_t)b * c->n_ctas;
+}
+
+// the update that is finished by a kernel launched with K: update f (its slot buffers, control block, inverse pose)
+void fill_finish(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long f) {
+    const int b = (int)(f & 1);
+    K.rec_fin = c->d_rec[b]; K.state_fin = c->d_state_c[b]; K.best_fin = c->d_best[b];
+    K.cta_fin = c->d_cta_cnt + (size_t)b * c->n_ctas;
+    K.ctrl_zero = c->d_ctrl + ((f + 2) % 3);
+    for (int i = 0; i < 4; ++i) K.qi[i] = c->pend_qi[i];
+    for (int i = 0; i < 3; ++i) K.ti[i] = c->pend_ti[i];
+    K.ti_norm = c->pend_ti_norm;
+}
+
+// Runs the fusion of the last update if it is still pending (the maps are about to be read or replaced).
+int flush_pending(dmf_ctx_impl *c) {
+    if (!c->pending) return DMF_OK;
+    CU(cudaSetDevice(c->device));
+    dmf::KParams K{};
+    fill_kparams(c, K, c->seq - 1);
+    fill_finish(c, K, c->seq - 1);
+    dmf::fuse_kernel<<<dim3(c->tiles_x, c->n_bands), dmf::TILE_PIX, 0, c->stream>>>(K);
+    CU(cudaGetLastError());
+    c->pending = false;
+    return DMF_OK;
+}
+
+// frame_ready: event after which the frame at d_curr is complete (NULL: it already is when this call is made).
+int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3],
+                  cudaEvent_t frame_ready, cudaEvent_t frame_consumed) {
+    const dmf_params &p = c->prm;
     const int rows = c->n_rows;
     if (rows > 0) {
+        // debug planes describe ONE update: with them on, every update is set up from the maps and fused at once
+        if (c->pending && c->flags_on) { int rc = flush_pending(c); if (rc) return rc; }
+        const unsigned long long u = c->seq;
+        const int b = (int)(u & 1);
+        dmf::KParams K{};
+        fill_kparams(c, K, u);
+        K.curr = d_curr; K.curr_pitch = curr_pitch;
+        for (int i = 0; i < 4; ++i) K.q[i] = q[i];
+        for (int i = 0; i < 3; ++i) K.t[i] = t[i];
+        const bool merged = c->pending;
+        if (merged) fill_finish(c, K, u - 1);  // inverse pose of update u-1 for the fusion part
         dim3 grid((K.wi + dmf::TILE_W - 1) / dmf::TILE_W, (rows + dmf::TILE_H - 1) / dmf::TILE_H);
         dim3 mgrid((p.width - 15 + dmf::MOM_THREADS - 1) / dmf::MOM_THREADS, (p.height - 8 + dmf::MOM_STRIP - 1) / dmf::MOM_STRIP);
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -164,7 +206,8 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         if (frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));
         if (ms != c->stream) CU(cudaStreamWaitEvent(ms, c->ev_tab_free[b], 0));  // ncc_kernel of two updates ago
         if (ev[0]) CU(cudaEventRecord(ev[0], c->stream));
-        dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
+        if (merged) dmf::advance_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);  // fusion of u-1 + setup of u
+        else dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
         if (frame_consumed) CU(cudaEventRecord(frame_consumed, ms));
@@ -176,10 +219,14 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         c->ncc_fn<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
         CU(cudaEventRecord(c->ev_tab_free[b], c->stream));
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
-        dmf::fuse_kernel<<<(c->n_pix + dmf::TILE_PIX - 1) / dmf::TILE_PIX, dmf::TILE_PIX, 0, c->stream>>>(K);
-        if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
         CU(cudaGetLastError());
-        c->ctrl_idx++;
+        // the fusion of this update stays pending: the next update's advance_kernel or flush_pending() runs it
+        se3_inverse(q, t, c->pend_qi, c->pend_ti);
+        c->pend_ti_norm = std::sqrt(c->pend_ti[0] * c->pend_ti[0] + (c->pend_ti[1] * c->pend_ti[1] + c->pend_ti[2] * c->pend_ti[2]));
+        c->pending = true;
+        c->seq++;
+        if (c->flags_on) { int rc = flush_pending(c); if (rc) return rc; }
+        if (ev[4]) CU(cudaEventRecord(ev[4], c->stream));
     } else if (frame_consumed) {
         CU(cudaEventRecord(frame_consumed, c->stream));
     }
@@ -309,15 +356,22 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
     {
         // scratch of the setup -> ncc -> fuse pipeline
         c->n_pix = (int)((W - 2 * (size_t)params->border) * (size_t)c->n_rows);
-        const size_t np = c->n_pix > 0 ? (size_t)c->n_pix : 1;
+        c->tiles_x = (int)((W - 2 * (size_t)params->border + dmf::TILE_W - 1) / dmf::TILE_W);
+        c->n_bands = (c->n_rows + dmf::TILE_H - 1) / dmf::TILE_H;
+        if (c->n_bands < 1) c->n_bands = 1;
+        c->n_ctas = c->tiles_x * c->n_bands;
+        c->n_slots = c->n_ctas * dmf::TILE_PIX;  // >= n_pix (edge tiles are partly empty)
+        const size_t np = (size_t)c->n_slots;
         const int n_max = (int)(2.0 * params->max_half_len / params->step) + 2;  // trip-count bound of ref:432
         const size_t max_full = (size_t)(n_max / dmf::CHUNK) + 1;
-        CUX(cudaMalloc(&c->d_rec, np * sizeof(dmf::PixelRec)));
-        CUX(cudaMalloc(&c->d_best, np * sizeof(unsigned long long)));
+        for (int b = 0; b < 2; ++b) {
+            CUX(cudaMalloc(&c->d_rec[b], np * sizeof(dmf::PixelRec)));
+            CUX(cudaMalloc(&c->d_best[b], np * sizeof(unsigned long long)));
+            CUX(cudaMalloc(&c->d_state_c[b], np * sizeof(double2)));
+        }
         CUX(cudaMalloc(&c->d_units_full, np * max_full * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
-        CUX(cudaMalloc(&c->d_ctrl, 2 * sizeof(dmf::Ctrl)));
-        CUX(cudaMalloc(&c->d_state_c, np * sizeof(double2)));
+        CUX(cudaMalloc(&c->d_ctrl, 3 * sizeof(dmf::Ctrl)));
         for (int b = 0; b < 2; ++b) {
             CUX(cudaMalloc(&c->d_mom1[b], W * H * sizeof(int4)));
             CUX(cudaMalloc(&c->d_mom2[b], W * H * sizeof(dmf::mom2_t)));
@@ -330,7 +384,9 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         }
         CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
-        CUX(cudaMemsetAsync(c->d_ctrl, 0, 2 * sizeof(dmf::Ctrl), c->stream));
+        CUX(cudaMemsetAsync(c->d_ctrl, 0, 3 * sizeof(dmf::Ctrl), c->stream));
+        CUX(cudaMalloc(&c->d_cta_cnt, 2 * (size_t)c->n_ctas * sizeof(unsigned int)));
+        CUX(cudaMemsetAsync(c->d_cta_cnt, 0, 2 * (size_t)c->n_ctas * sizeof(unsigned int), c->stream));
         int per_sm = 0;
         switch (params->width) {  // compile-time widths: the row loads of a sample become immediate offsets
             case 640: c->ncc_fn = dmf::ncc_kernel<640>; break;
@@ -384,7 +440,8 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_best); cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_state_c); cudaFree(ctx->d_refx);
+    for (int b = 0; b < 2; ++b) { cudaFree(ctx->d_rec[b]); cudaFree(ctx->d_best[b]); cudaFree(ctx->d_state_c[b]); }
+    cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_cta_cnt); cudaFree(ctx->d_refx);
     for (int b = 0; b < 2; ++b) {
         cudaFree(ctx->d_mom1[b]); cudaFree(ctx->d_mom2[b]); cudaFree(ctx->d_currx[b]);
         if (ctx->ev_mom_done[b]) cudaEventDestroy(ctx->ev_mom_done[b]);
@@ -426,6 +483,7 @@ int dmf_set_reference(dmf_ctx *c, const uint8_t *ref_host, size_t step) {
     if (!c || !ref_host) return fail(c, DMF_ERR_INVALID, "dmf_set_reference: NULL argument");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_set_reference: step < width");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     CU(cudaMemcpy2DAsync(c->d_ref, c->img_pitch, ref_host, step, c->prm.width, c->prm.height, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // the host image may be released on return
     return run_ref_stats(c);
@@ -435,6 +493,7 @@ int dmf_set_reference_device(dmf_ctx *c, const uint8_t *ref_dev, size_t step) {
     if (!c || !ref_dev) return fail(c, DMF_ERR_INVALID, "dmf_set_reference_device: NULL argument");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_set_reference_device: step < width");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     CU(cudaMemcpy2DAsync(c->d_ref, c->img_pitch, ref_dev, step, c->prm.width, c->prm.height, cudaMemcpyDeviceToDevice, c->stream));
     return run_ref_stats(c);
 }
@@ -442,6 +501,7 @@ int dmf_set_reference_device(dmf_ctx *c, const uint8_t *ref_dev, size_t step) {
 int dmf_fill_state(dmf_ctx *c, double init_depth, double init_cov2) {
     if (!c) return fail(c, DMF_ERR_INVALID, "dmf_fill_state: NULL context");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     const size_t n = (size_t)c->prm.width * c->prm.height;
     dmf::fill_state_kernel<<<148 * 4, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, n, init_depth, init_cov2);
     CU(cudaGetLastError());
@@ -453,6 +513,7 @@ int dmf_upload_state(dmf_ctx *c, const double *depth, size_t depth_step, const d
     const size_t rowb = (size_t)c->prm.width * sizeof(double);
     if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_upload_state: step < width*8");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     for (const auto &sp : c->io_spans) {
         const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync(c->d_depth + (size_t)y0 * c->prm.width, rowb, (const char *)depth + (size_t)y0 * depth_step, depth_step, rowb, rows, cudaMemcpyHostToDevice, c->stream));
@@ -467,6 +528,7 @@ int dmf_download_state(dmf_ctx *c, double *depth, size_t depth_step, double *cov
     const size_t rowb = (size_t)c->prm.width * sizeof(double);
     if (depth_step < rowb || cov2_step < rowb) return fail(c, DMF_ERR_INVALID, "dmf_download_state: step < width*8");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     for (const auto &sp : c->io_spans) {
         const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync((char *)depth + (size_t)y0 * depth_step, depth_step, c->d_depth + (size_t)y0 * c->prm.width, rowb, rowb, rows, cudaMemcpyDeviceToHost, c->stream));
@@ -528,9 +590,15 @@ int dmf_update_device(dmf_ctx *c, const uint8_t *curr_dev, size_t step, const do
     return launch_update(c, c->d_curr[b], c->img_pitch, q, t, c->ev_copied[b], c->ev_consumed[b]);
 }
 
+int dmf_flush(dmf_ctx *c) {
+    if (!c) return fail(c, DMF_ERR_INVALID, "dmf_flush: NULL context");
+    return flush_pending(c);
+}
+
 int dmf_sync(dmf_ctx *c) {
     if (!c) return fail(c, DMF_ERR_INVALID, "dmf_sync: NULL context");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->mom_stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -540,6 +608,7 @@ int dmf_sync(dmf_ctx *c) {
 int dmf_read_counters(dmf_ctx *c, dmf_counters *out, int reset) {
     if (!c || !out) return fail(c, DMF_ERR_INVALID, "dmf_read_counters: NULL argument");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     unsigned long long h[3];
     CU(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     if (reset) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
@@ -579,6 +648,7 @@ int dmf_get_timing(dmf_ctx *c, double ms_out[4], uint64_t *frames, int reset) {
 int dmf_enable_flags(dmf_ctx *c, int enable) {
     if (!c) return fail(c, DMF_ERR_INVALID, "dmf_enable_flags: NULL context");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     if (enable && !c->d_dbg_ncc) {
         const size_t n = (size_t)c->prm.width * c->prm.height;
         CU(cudaMalloc(&c->d_dbg_ncc, n * sizeof(float)));
@@ -594,6 +664,7 @@ int dmf_download_flags(dmf_ctx *c, uint8_t *flags_host, size_t step) {
     if (!c || !flags_host) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: NULL argument");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_download_flags: step < width");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     for (const auto &sp : c->io_spans) {
         const int y0 = sp.first, rows = sp.second - sp.first;
         CU(cudaMemcpy2DAsync(flags_host + (size_t)y0 * step, step, c->d_flags + (size_t)y0 * c->prm.width, c->prm.width, c->prm.width, rows, cudaMemcpyDeviceToHost, c->stream));
@@ -606,6 +677,7 @@ int dmf_download_debug(dmf_ctx *c, float *best_ncc_host, int32_t *samples_host) 
     if (!c || !best_ncc_host || !samples_host) return fail(c, DMF_ERR_INVALID, "dmf_download_debug: NULL argument");
     if (!c->d_dbg_ncc) return fail(c, DMF_ERR_STATE, "dmf_download_debug: dmf_enable_flags(ctx, 1) has not been called");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     const size_t n = (size_t)c->prm.width * c->prm.height;
     CU(cudaMemcpyAsync(best_ncc_host, c->d_dbg_ncc, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(samples_host, c->d_dbg_n, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -615,6 +687,7 @@ int dmf_download_debug(dmf_ctx *c, float *best_ncc_host, int32_t *samples_host) 
 
 int dmf_device_state(dmf_ctx *c, double **depth_dev, double **cov2_dev, size_t *pitch) {
     if (!c || !depth_dev || !cov2_dev || !pitch) return fail(c, DMF_ERR_INVALID, "dmf_device_state: NULL argument");
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     *depth_dev = c->d_depth; *cov2_dev = c->d_cov2; *pitch = (size_t)c->prm.width * sizeof(double);
     return DMF_OK;
 }
@@ -654,6 +727,7 @@ int dmf_evaluate_depth(dmf_ctx *c, double max_variance, double *sum_sq, uint64_t
     if (!c || !sum_sq || !count) return fail(c, DMF_ERR_INVALID, "dmf_evaluate_depth: NULL argument");
     if (!c->have_truth) return fail(c, DMF_ERR_STATE, "dmf_evaluate_depth: dmf_set_truth() has not been called");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     CU(cudaMemsetAsync(c->d_eval, 0, sizeof(double), c->stream));
     CU(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
     for (const auto &sp : c->spans) {
@@ -674,6 +748,7 @@ int dmf_variance_mask(dmf_ctx *c, double max_variance, uint8_t *mask_host, size_
     if (!c || !mask_host) return fail(c, DMF_ERR_INVALID, "dmf_variance_mask: NULL argument");
     if (step < (size_t)c->prm.width) return fail(c, DMF_ERR_INVALID, "dmf_variance_mask: step < width");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     const int W = c->prm.width;
     if (!c->d_mask) CU(cudaMalloc(&c->d_mask, (size_t)W * c->prm.height));
     for (const auto &sp : c->io_spans) {
@@ -695,6 +770,7 @@ int dmf_point_cloud(dmf_ctx *c, const uint8_t *color_host, size_t color_step, in
     if (color_step < (size_t)p.width * channels) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: step < width*channels");
     if (c->cyc != 1) return fail(c, DMF_ERR_STATE, "dmf_point_cloud: needs a context that owns a contiguous band");
     CU(cudaSetDevice(c->device));
+    { int rc_ = flush_pending(c); if (rc_) return rc_; }
     const int y0 = c->row0, n_rows = c->n_rows;
     *n_points = 0;
     if (n_rows <= 0) return DMF_OK;

@@ -77,14 +77,14 @@ constexpr unsigned KEY_SENTINEL_LO = 511u;
 
 // Per-frame control block in HBM.
 struct Ctrl {
-    unsigned int count[CHUNK + 1];  // count[L] = number of units of length L (L = 1..CHUNK); count[0] = active pixels
+    unsigned int count[CHUNK + 1];  // count[L] = number of units of length L (L = 1..CHUNK)
     unsigned int cursor;            // next unclaimed slot of the padded, concatenated lists
     unsigned int pad[6];
 };
 
 // Record of one ACTIVE pixel of one frame (64 B = half a cache line, four 16-byte vectors): everything
 // ncc_kernel / fuse_kernel need about it, so a work unit starts with ONE line fetch.  Records are compacted:
-// setup_kernel gives every active pixel a slot (CTA-aggregated counter), units and fuse_kernel address slots.
+// every active pixel gets a slot in its band's slot range (CTA-aggregated counters), units and the fusion address slots.
 struct __align__(16) PixelRec {
     double2 pm;        // px_mean_curr ref:406
     double2 dir;       // epipolar_direction ref:419-420
@@ -132,8 +132,19 @@ struct KParams {
     unsigned long long *best;                      // arg-max keys
     unsigned int *units_full;                      // units of length CHUNK
     unsigned int *units_tail;                      // (CHUNK-1) lists of capacity n_pix: lengths 1..CHUNK-1
-    Ctrl *ctrl;                                    // this frame's control block
-    Ctrl *ctrl_next;                               // the next frame's (re-armed by fuse_kernel)
+    Ctrl *ctrl;                                    // control block of the frame being set up / searched
+    Ctrl *ctrl_zero;                               // control block re-armed by the kernel that finishes a frame
+    // Slot space: CTA c of the pixel grid (a TILE_W x TILE_H tile of the band) owns the slots [c * TILE_PIX,
+    // (c + 1) * TILE_PIX) for the whole sequence and keeps its cta_cnt[c] active pixels packed at the front, in tile
+    // scan order.  No counter is shared between CTAs, and slot order never drifts away from image order (with shared
+    // counters the arrival-order shuffle compounds from update to update: measured -28 % in ncc_kernel from the lost
+    // L1/L2 locality, -17 % even with one counter per 8-row band).
+    unsigned int *cta_cnt;                         // of the update being set up
+    // the frame being FINISHED by fuse_kernel / advance_kernel (records, state, keys, per-CTA counts of its slots)
+    const PixelRec *rec_fin;
+    const double2 *state_fin;
+    const unsigned long long *best_fin;
+    const unsigned int *cta_fin;
     uint8_t *flags;
     float *dbg_ncc;  // with write_flags: best NCC per active pixel (rounded to f32)
     int *dbg_n;      // with write_flags: (trip count << 16) | winning iteration (0xFFFF: none)
@@ -260,55 +271,48 @@ __device__ __forceinline__ void search_geometry(const KParams &P, int x, int y, 
 }
 
 // ----------------------------------------------------------------------------------------
-// K2a: per-pixel setup + compaction of the active pixels + work-unit emission.
-__global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__ KParams P) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
-    const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
-    const bool in_img = (x < P.width - P.border) && (rl < P.n_rows);
-    const int y = row_of(P, rl);
-
-    int n = 0;
-    bool active = false;
-    double mu = 0, c2 = 0, pmx = 0, pmy = 0, lx = 0, ly = 0, half = 0;
-    int2 st = make_int2(0, 0);
-    if (in_img) {
-        c2 = P.cov2[(size_t)y * P.state_pitch + x];
-        mu = P.depth[(size_t)y * P.state_pitch + x];  // issued with the cov load: one round trip
-        active = !(c2 < P.min_cov || c2 > P.max_cov);  // ref:366 — NaN passes the gate
-        if (active) {
-            search_geometry(P, x, y, mu, c2, pmx, pmy, lx, ly, half);
-            // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
-            if (half >= 0) {
-                n = (int)(2.0 * half * P.inv_step) + 1;
-                while (n > 0 && sample_l(half, P.step, n - 1) > half) --n;
-                while (n < 100000 && sample_l(half, P.step, n) <= half) ++n;
-            }
-            st = __ldg(&P.refstat[(size_t)y * P.stat_pitch + x]);
+// Per-pixel setup of one update, shared by setup_kernel (thread = pixel, state read from the maps) and advance_kernel
+// (thread = slot of the previous update, state straight from its fusion).
+struct PixelWork {
+    bool active;
+    int x, y, n;                         // pixel, trip count of the search loop
+    double mu, c2;                       // state (ref:366)
+    double pmx, pmy, lx, ly, half;       // epipolar segment
+    int2 st;                             // reference-patch statistics
+};
+__device__ __forceinline__ void prepare_pixel(const KParams &P, PixelWork &w, bool have) {
+    w.n = 0; w.pmx = w.pmy = w.lx = w.ly = w.half = 0; w.st = make_int2(0, 0);
+    w.active = have && !(w.c2 < P.min_cov || w.c2 > P.max_cov);  // ref:366 — NaN passes the gate
+    if (w.active) {
+        search_geometry(P, w.x, w.y, w.mu, w.c2, w.pmx, w.pmy, w.lx, w.ly, w.half);
+        // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
+        if (w.half >= 0) {
+            int n = (int)(2.0 * w.half * P.inv_step) + 1;
+            while (n > 0 && sample_l(w.half, P.step, n - 1) > w.half) --n;
+            while (n < 100000 && sample_l(w.half, P.step, n) <= w.half) ++n;
+            w.n = n;
         }
-        if (P.write_flags) {  // debug planes: fuse_kernel only visits active pixels
-            const size_t o = (size_t)y * P.flags_pitch + x;
-            P.dbg_n[o] = n;
-            if (!active) { P.flags[o] = 0; P.dbg_ncc[o] = 0.0f; }
-        }
+        w.st = __ldg(&P.refstat[(size_t)w.y * P.stat_pitch + w.x]);
     }
+}
 
-    // ---- slots and work units.  Space is claimed once per CTA and per list (thread L does the atomicAdd for list L,
-    // thread 0 the one for the active-pixel slots, so the latency is paid once per CTA instead of by every warp);
-    // every warp then writes its units chunk-major so that adjacent list entries hold adjacent pixels of one image row.
+// Compaction + work-unit emission; must be reached by every thread of the CTA (two barriers).  Space is claimed once
+// per CTA and per list (thread L does the atomicAdd for list L, thread 0 the one for the active-pixel slots, so the
+// latency is paid once per CTA instead of by every warp); every warp then writes its units chunk-major so that
+// adjacent list entries hold neighbouring pixels.
+__device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w) {
     __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
     __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first entry of that warp in list L / first slot
-    const int warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int n_full = n / CHUNK, tail = n % CHUNK;
+    const int n_full = w.n / CHUNK, tail = w.n % CHUNK;
     const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
     const int m_full = __reduce_max_sync(0xffffffffu, n_full);
     // lanes with the same tail length form a group (one MATCH instead of CHUNK-1 ballots): rank inside the group,
     // and the group's first lane posts its size
     const unsigned peers = __match_any_sync(0xffffffffu, tail);
     const unsigned my_rank = (unsigned)__popc(peers & lt_mask);
-    const unsigned act_bal = __ballot_sync(0xffffffffu, active);
+    const unsigned act_bal = __ballot_sync(0xffffffffu, w.active);
     if (lane <= CHUNK) s_cnt[warp][lane] = (lane == 0) ? (unsigned)__popc(act_bal) : (lane == CHUNK) ? (unsigned)tot_full : 0u;
     __syncwarp();
     if (tail > 0 && my_rank == 0) s_cnt[warp][tail] = (unsigned)__popc(peers);
@@ -316,20 +320,23 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     if (tid <= CHUNK) {
         unsigned pre[TILE_PIX / 32], tot = 0;
 #pragma unroll
-        for (int w = 0; w < TILE_PIX / 32; ++w) { pre[w] = tot; tot += s_cnt[w][tid]; }
-        const unsigned base = tot ? atomicAdd(&P.ctrl->count[tid], tot) : 0u;
+        for (int k = 0; k < TILE_PIX / 32; ++k) { pre[k] = tot; tot += s_cnt[k][tid]; }
+        const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+        unsigned base = cta * TILE_PIX;                     // tid 0: the CTA's own slot range
+        if (tid == 0) P.cta_cnt[cta] = tot;
+        else base = tot ? atomicAdd(&P.ctrl->count[tid], tot) : 0u;
 #pragma unroll
-        for (int w = 0; w < TILE_PIX / 32; ++w) s_base[w][tid] = base + pre[w];
+        for (int k = 0; k < TILE_PIX / 32; ++k) s_base[k][tid] = base + pre[k];
     }
     __syncthreads();
     const unsigned slot = s_base[warp][0] + (unsigned)__popc(act_bal & lt_mask);
-    if (active) {
+    if (w.active) {
         PixelRec *rec = P.rec + slot;  // four 16-byte vector stores
-        rec->pm = make_double2(pmx, pmy);
-        rec->dir = make_double2(lx, ly);
-        *reinterpret_cast<int4 *>(&rec->half) = make_int4(__double2loint(half), __double2hiint(half), -st.x, st.y);
-        rec->xy = make_int4(x, y, 0, 0);
-        P.state_c[slot] = make_double2(mu, c2);
+        rec->pm = make_double2(w.pmx, w.pmy);
+        rec->dir = make_double2(w.lx, w.ly);
+        *reinterpret_cast<int4 *>(&rec->half) = make_int4(__double2loint(w.half), __double2hiint(w.half), -w.st.x, w.st.y);
+        rec->xy = make_int4(w.x, w.y, 0, 0);
+        P.state_c[slot] = make_double2(w.mu, w.c2);
         P.best[slot] = key_init();
     }
     if (m_full > 0) {
@@ -342,6 +349,29 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     }
     if (tail > 0)
         P.units_tail[(size_t)(tail - 1) * P.n_pix + s_base[warp][tail] + my_rank] = (slot << CHUNK_BITS) | (unsigned)n_full;
+}
+
+// K2a: setup of an update from the maps (thread = pixel): the first update after the state was loaded, or any update
+// whose predecessor has already been fused (strict drop-in mode, debug planes on).
+__global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__ KParams P) {
+    const int tid = threadIdx.x;
+    PixelWork w;
+    w.x = P.border + blockIdx.x * TILE_W + (tid % TILE_W);
+    const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
+    const bool in_img = (w.x < P.width - P.border) && (rl < P.n_rows);
+    w.y = row_of(P, rl);
+    w.mu = 0; w.c2 = 0;
+    if (in_img) {
+        w.c2 = P.cov2[(size_t)w.y * P.state_pitch + w.x];
+        w.mu = P.depth[(size_t)w.y * P.state_pitch + w.x];  // issued with the cov load: one round trip
+    }
+    prepare_pixel(P, w, in_img);
+    if (in_img && P.write_flags) {  // debug planes: fuse_kernel only visits active pixels
+        const size_t o = (size_t)w.y * P.flags_pitch + w.x;
+        P.dbg_n[o] = w.n;
+        if (!w.active) { P.flags[o] = 0; P.dbg_ncc[o] = 0.0f; }
+    }
+    emit_pixel(P, w);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -663,77 +693,97 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
 }
 
 // ----------------------------------------------------------------------------------------
-// K2c: accept test + depth-filter fusion over the compacted active pixels (thread = slot), in place on the maps.
-// Key, record and the state setup_kernel read arrive in ONE round trip.  Also re-arms the next frame's control block.
+// Accept test ref:443 + updateDepthFilter ref:482-567 of one slot of the frame being finished: key, record and the
+// state setup read arrive in ONE round trip.  Writes the fused state to the maps and returns it in (mu, c2).
+__device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &x, int &y, double &mu, double &c2,
+                                          unsigned long long &key) {
+    key = P.best_fin[slot];
+    const PixelRec *rec = P.rec_fin + slot;
+    const double2 pm = rec->pm, dir = rec->dir;
+    const double half = rec->half;
+    const int4 xy = rec->xy;
+    const double2 mc = P.state_fin[slot];
+    mu = mc.x; c2 = mc.y;
+    x = xy.x; y = xy.y;
+    const bool accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
+    if (accepted) {
+        const int k = key_index(key);
+        const double ex = dir.x, ey = dir.y;
+        const double l = sample_l(half, P.step, k);
+        const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
+        // updateDepthFilter ref:482-567
+        const D3 f_ref = unit_ray(P, (double)x, (double)y);
+        const D3 f_curr = unit_ray(P, cxp, cyp);
+        const D3 t{P.ti[0], P.ti[1], P.ti[2]};
+        const D3 f2 = qrot(P.qi, f_curr);
+        const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
+        const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
+        const double a10 = -a01;
+        // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
+        const double rdet = 1.0 / (a00 * a11 - a01 * a10);
+        const double ans0 = (b0 * a11 - a01 * b1) * rdet;
+        const double ans1 = (a00 * b1 - a10 * b0) * rdet;
+        const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
+                    0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
+        const double depth_est = sqrt(dot3(pe, pe));
+        // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
+        // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
+        // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
+        // transcendental call (|c| > 1 by rounding gives NaN on both routes).
+        const double t_norm = P.ti_norm;
+        const double rt = 1.0 / t_norm;
+        const double ca = dot3(f_ref, t) * rt;
+        const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
+        const double cb = -dot3(fcp, t) * rt;
+        const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
+        const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
+        const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
+        const double d_cov2 = d_cov * d_cov;
+        const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
+        const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
+        const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
+        const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
+        const double sig_fuse = (c2 * d_cov2) * rden;
+        mu = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
+        c2 = sig_fuse;                                   // ref:564
+        P.depth[(size_t)y * P.state_pitch + x] = mu;
+        P.cov2[(size_t)y * P.state_pitch + x] = c2;
+    }
+    return accepted;
+}
+
+// counters of the finished frame: warp ballots -> shared -> ONE global atomic per CTA and counter (same-address
+// atomics from every warp serialise in L2 and were the critical path of this kernel)
+__device__ __forceinline__ void count_frame(const KParams &P, unsigned n_fin, bool accepted) {
+    __shared__ unsigned s_acc;
+    if (threadIdx.x == 0) s_acc = 0;
+    __syncthreads();
+    const unsigned c = __popc(__ballot_sync(0xffffffffu, accepted));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_acc, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&P.counters[0], (unsigned long long)n_fin);
+        if (s_acc) atomicAdd(&P.counters[2], (unsigned long long)s_acc);
+    }
+}
+
+// K2c: finishes a frame on its own (same grid as setup_kernel, thread = slot of the CTA's range): accept test + fusion,
+// in place on the maps.  Used when the maps are read before the next update (end of a sequence, strict drop-in mode,
+// debug planes).
 #ifndef DMF_FUSE_MIN_BLOCKS
 #define DMF_FUSE_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(const __grid_constant__ KParams P) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const unsigned n_active = P.ctrl->count[0];
-    if (blockIdx.x == 0) {
-        if (tid < (int)(sizeof(Ctrl) / sizeof(unsigned))) reinterpret_cast<unsigned *>(P.ctrl_next)[tid] = 0;
-        if (tid == 0 && n_active) atomicAdd(&P.counters[0], (unsigned long long)n_active);
-    }
-    const unsigned slot = blockIdx.x * TILE_PIX + tid;
-    if (blockIdx.x * TILE_PIX >= n_active) return;  // CTA-uniform
-    const bool active = slot < n_active;
-
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta == 0 && threadIdx.x < sizeof(Ctrl) / sizeof(unsigned)) reinterpret_cast<unsigned *>(P.ctrl_zero)[threadIdx.x] = 0;
+    const unsigned n_fin = P.cta_fin[cta];
+    if (n_fin == 0) return;  // CTA-uniform
     bool accepted = false;
-    unsigned long long key = 0;
-    int x = 0, y = 0;
-    if (active) {
-        key = P.best[slot];
-        const PixelRec *rec = P.rec + slot;
-        const double2 pm = rec->pm, dir = rec->dir;
-        const double half = rec->half;
-        const int4 xy = rec->xy;
-        const double2 mc = P.state_c[slot];
-        const double mu = mc.x, c2 = mc.y;
-        x = xy.x; y = xy.y;
-        accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
-        if (accepted) {
-            const int k = key_index(key);
-            const double ex = dir.x, ey = dir.y;
-            const double l = sample_l(half, P.step, k);
-            const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
-            // updateDepthFilter ref:482-567
-            const D3 f_ref = unit_ray(P, (double)x, (double)y);
-            const D3 f_curr = unit_ray(P, cxp, cyp);
-            const D3 t{P.ti[0], P.ti[1], P.ti[2]};
-            const D3 f2 = qrot(P.qi, f_curr);
-            const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
-            const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
-            const double a10 = -a01;
-            // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
-            const double rdet = 1.0 / (a00 * a11 - a01 * a10);
-            const double ans0 = (b0 * a11 - a01 * b1) * rdet;
-            const double ans1 = (a00 * b1 - a10 * b0) * rdet;
-            const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
-                        0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
-            const double depth_est = sqrt(dot3(pe, pe));
-            // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
-            // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
-            // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
-            // transcendental call (|c| > 1 by rounding gives NaN on both routes).
-            const double t_norm = P.ti_norm;
-            const double rt = 1.0 / t_norm;
-            const double ca = dot3(f_ref, t) * rt;
-            const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
-            const double cb = -dot3(fcp, t) * rt;
-            const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
-            const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
-            const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
-            const double d_cov2 = d_cov * d_cov;
-            const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
-            const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
-            const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
-            const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
-            const double sig_fuse = (c2 * d_cov2) * rden;
-            P.depth[(size_t)y * P.state_pitch + x] = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
-            P.cov2[(size_t)y * P.state_pitch + x] = sig_fuse;                                    // ref:564
-        }
+    if (threadIdx.x < n_fin) {
+        int x, y;
+        double mu, c2;
+        unsigned long long key;
+        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, x, y, mu, c2, key);
         if (P.write_flags) {
             const size_t o = (size_t)y * P.flags_pitch + x;
             P.flags[o] = (uint8_t)(1 | (accepted ? 2 : 0));
@@ -743,15 +793,33 @@ __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(con
             P.dbg_n[o] = (trips << 16) | (int)kb;
         }
     }
-    // accepted counter: warp ballots -> shared -> ONE global atomic per CTA (same-address atomics from
-    // every warp serialise in L2 and were the critical path of this kernel)
-    __shared__ unsigned s_acc;
-    if (tid == 0) s_acc = 0;
-    __syncthreads();
-    const unsigned c = __popc(__ballot_sync(0xffffffffu, accepted));
-    if (lane == 0 && c) atomicAdd(&s_acc, c);
-    __syncthreads();
-    if (tid == 0 && s_acc) atomicAdd(&P.counters[2], (unsigned long long)s_acc);
+    count_frame(P, n_fin, accepted);
+}
+
+// K2d: finishes update k AND sets up update k+1 (same grid as setup_kernel, thread = slot of update k).  A pixel that
+// fails the gate ref:366 is never written again, so it stays inactive for the rest of the sequence: only the slots of
+// update k can be active in update k+1.  The fused state goes from registers straight into the next search geometry;
+// the maps are written but not read, and the converged / diverged pixels cost nothing any more.  P.q/P.t: pose of
+// update k+1 (setup part); P.qi/P.ti/P.ti_norm: inverse pose of update k (fusion part).
+__global__ void __launch_bounds__(TILE_PIX) advance_kernel(const __grid_constant__ KParams P) {
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta == 0 && threadIdx.x < sizeof(Ctrl) / sizeof(unsigned)) reinterpret_cast<unsigned *>(P.ctrl_zero)[threadIdx.x] = 0;
+    const unsigned n_fin = P.cta_fin[cta];
+    if (n_fin == 0) {  // CTA-uniform: nothing left in this tile
+        if (threadIdx.x == 0) P.cta_cnt[cta] = 0;
+        return;
+    }
+    const bool have = threadIdx.x < n_fin;
+    bool accepted = false;
+    PixelWork w;
+    w.x = 0; w.y = 0; w.mu = 0; w.c2 = 0;
+    if (have) {
+        unsigned long long key;
+        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, w.x, w.y, w.mu, w.c2, key);
+    }
+    count_frame(P, n_fin, accepted);
+    prepare_pixel(P, w, have);
+    emit_pixel(P, w);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -163,6 +163,10 @@ class DepthFilter:
         self._ck(self._lib.dmf_update_device(self._ctx, C.c_void_p(dev_ptr), step, q, t,
                                              C.c_void_p(wait_stream) if wait_stream else None), "dmf_update_device")
 
+    def flush(self) -> None:
+        """Enqueue the deferred fusion of the last update (asynchronous); every accessor does this implicitly."""
+        self._ck(self._lib.dmf_flush(self._ctx), "dmf_flush")
+
     def sync(self) -> None:
         self._ck(self._lib.dmf_sync(self._ctx), "dmf_sync")
 

@@ -225,6 +225,11 @@ class ShardedDepthFilter:
     def _sync_filter(self) -> None:
         self.filter.sync()
 
+    def flush(self) -> None:
+        """Enqueue the deferred fusion of the last update on the context stream (asynchronous)."""
+        if hasattr(self.filter, "flush"):
+            self.filter.flush()
+
     def _local_counters(self, reset: bool) -> dict:
         return self.filter.counters(reset)
 

@@ -35,6 +35,7 @@ for lib in libs:
             e0.record(st)
             for i in range(1, n):
                 f.update_device(frames[i].data_ptr(), pitch, poses[i])
+            f.flush()
             e1.record(st); f.sync()
             ms = e0.elapsed_time(e1); c = f.counters()
             if r > 0: best = min(best, ms)
