@@ -154,6 +154,7 @@ void fill_finish(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long f) {
     for (int i = 0; i < 4; ++i) K.qi[i] = c->pend_qi[i];
     for (int i = 0; i < 3; ++i) K.ti[i] = c->pend_ti[i];
     K.ti_norm = c->pend_ti_norm;
+    K.inv_ti_norm = 1.0 / c->pend_ti_norm;
 }
 
 // Runs the fusion of the last update if it is still pending (the maps are about to be read or replaced).

@@ -116,6 +116,7 @@ struct KParams {
     double q[4], t[3];    // T_C_R (unit quaternion x,y,z,w + translation)
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
     double ti_norm;       // |t_RC| (ref:525)
+    double inv_ti_norm;   // 1 / |t_RC| (host-side division)
     double bd, wd, hd;    // border, width, height as doubles (inside() ref:222-224 without per-sample I2F)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
     const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (moments_kernel)
@@ -241,10 +242,10 @@ __device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v) {
 }
 
 // Epipolar search geometry of pixel (x,y) with state (mu, c2): ref:402-422.
-__device__ __forceinline__ void search_geometry(const KParams &P, int x, int y, double mu, double c2, double &pmx, double &pmy,
+// f_ref: unit ray of the pixel, ref:402-403 (the caller may already hold it)
+__device__ __forceinline__ void search_geometry(const KParams &P, const D3 &f_ref, double mu, double c2, double &pmx, double &pmy,
                                              double &lx, double &ly, double &half) {
     const double sigma = sqrt(c2);  // ref:377
-    const D3 f_ref = unit_ray(P, (double)x, (double)y);  // ref:402-403
     const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
     double d_min, d_max;
     if (P.inverse_depth) {  // ref:407-410
@@ -279,12 +280,15 @@ struct PixelWork {
     double mu, c2;                       // state (ref:366)
     double pmx, pmy, lx, ly, half;       // epipolar segment
     int2 st;                             // reference-patch statistics
+    D3 f_ref;                            // unit ray of the pixel (valid if have_ray)
+    bool have_ray;
 };
 __device__ __forceinline__ void prepare_pixel(const KParams &P, PixelWork &w, bool have) {
     w.n = 0; w.pmx = w.pmy = w.lx = w.ly = w.half = 0; w.st = make_int2(0, 0);
     w.active = have && !(w.c2 < P.min_cov || w.c2 > P.max_cov);  // ref:366 — NaN passes the gate
     if (w.active) {
-        search_geometry(P, w.x, w.y, w.mu, w.c2, w.pmx, w.pmy, w.lx, w.ly, w.half);
+        if (!w.have_ray) w.f_ref = unit_ray(P, (double)w.x, (double)w.y);
+        search_geometry(P, w.f_ref, w.mu, w.c2, w.pmx, w.pmy, w.lx, w.ly, w.half);
         // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
         if (w.half >= 0) {
             int n = (int)(2.0 * w.half * P.inv_step) + 1;
@@ -300,8 +304,9 @@ __device__ __forceinline__ void prepare_pixel(const KParams &P, PixelWork &w, bo
 // per CTA and per list (thread L does the atomicAdd for list L, thread 0 the one for the active-pixel slots, so the
 // latency is paid once per CTA instead of by every warp); every warp then writes its units chunk-major so that
 // adjacent list entries hold neighbouring pixels.
-__device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w) {
-    __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 1];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
+// `accepted` / `n_fin` (advance_kernel): the finished frame's counters ride on the same CTA-wide aggregation.
+__device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w, bool accepted = false, unsigned n_fin = 0) {
+    __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 2];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
     __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first entry of that warp in list L / first slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -313,7 +318,8 @@ __device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w)
     const unsigned peers = __match_any_sync(0xffffffffu, tail);
     const unsigned my_rank = (unsigned)__popc(peers & lt_mask);
     const unsigned act_bal = __ballot_sync(0xffffffffu, w.active);
-    if (lane <= CHUNK) s_cnt[warp][lane] = (lane == 0) ? (unsigned)__popc(act_bal) : (lane == CHUNK) ? (unsigned)tot_full : 0u;
+    const unsigned acc_bal = __ballot_sync(0xffffffffu, accepted);
+    if (lane <= CHUNK + 1) s_cnt[warp][lane] = (lane == 0) ? (unsigned)__popc(act_bal) : (lane == CHUNK) ? (unsigned)tot_full : (lane == CHUNK + 1) ? (unsigned)__popc(acc_bal) : 0u;
     __syncwarp();
     if (tail > 0 && my_rank == 0) s_cnt[warp][tail] = (unsigned)__popc(peers);
     __syncthreads();
@@ -327,6 +333,12 @@ __device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w)
         else base = tot ? atomicAdd(&P.ctrl->count[tid], tot) : 0u;
 #pragma unroll
         for (int k = 0; k < TILE_PIX / 32; ++k) s_base[k][tid] = base + pre[k];
+    } else if (tid == CHUNK + 1 && n_fin) {  // counters of the finished frame: active, accepted
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < TILE_PIX / 32; ++k) acc += s_cnt[k][CHUNK + 1];
+        atomicAdd(&P.counters[0], (unsigned long long)n_fin);
+        if (acc) atomicAdd(&P.counters[2], (unsigned long long)acc);
     }
     __syncthreads();
     const unsigned slot = s_base[warp][0] + (unsigned)__popc(act_bal & lt_mask);
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
     const int rl = blockIdx.y * TILE_H + (tid / TILE_W);
     const bool in_img = (w.x < P.width - P.border) && (rl < P.n_rows);
     w.y = row_of(P, rl);
-    w.mu = 0; w.c2 = 0;
+    w.mu = 0; w.c2 = 0; w.have_ray = false;
     if (in_img) {
         w.c2 = P.cov2[(size_t)w.y * P.state_pitch + w.x];
         w.mu = P.depth[(size_t)w.y * P.state_pitch + w.x];  // issued with the cov load: one round trip
@@ -696,7 +708,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
 // Accept test ref:443 + updateDepthFilter ref:482-567 of one slot of the frame being finished: key, record and the
 // state setup read arrive in ONE round trip.  Writes the fused state to the maps and returns it in (mu, c2).
 __device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &x, int &y, double &mu, double &c2,
-                                          unsigned long long &key) {
+                                          unsigned long long &key, D3 &f_ref_out, bool &have_ray) {
     key = P.best_fin[slot];
     const PixelRec *rec = P.rec_fin + slot;
     const double2 pm = rec->pm, dir = rec->dir;
@@ -705,6 +717,7 @@ __device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &
     const double2 mc = P.state_fin[slot];
     mu = mc.x; c2 = mc.y;
     x = xy.x; y = xy.y;
+    have_ray = false;
     const bool accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
     if (accepted) {
         const int k = key_index(key);
@@ -713,6 +726,7 @@ __device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &
         const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
         // updateDepthFilter ref:482-567
         const D3 f_ref = unit_ray(P, (double)x, (double)y);
+        f_ref_out = f_ref; have_ray = true;
         const D3 f_curr = unit_ray(P, cxp, cyp);
         const D3 t{P.ti[0], P.ti[1], P.ti[2]};
         const D3 f2 = qrot(P.qi, f_curr);
@@ -731,7 +745,7 @@ __device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &
         // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
         // transcendental call (|c| > 1 by rounding gives NaN on both routes).
         const double t_norm = P.ti_norm;
-        const double rt = 1.0 / t_norm;
+        const double rt = P.inv_ti_norm;
         const double ca = dot3(f_ref, t) * rt;
         const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
         const double cb = -dot3(fcp, t) * rt;
@@ -783,7 +797,9 @@ __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(con
         int x, y;
         double mu, c2;
         unsigned long long key;
-        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, x, y, mu, c2, key);
+        D3 ray;
+        bool have_ray;
+        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, x, y, mu, c2, key, ray, have_ray);
         if (P.write_flags) {
             const size_t o = (size_t)y * P.flags_pitch + x;
             P.flags[o] = (uint8_t)(1 | (accepted ? 2 : 0));
@@ -812,14 +828,13 @@ __global__ void __launch_bounds__(TILE_PIX) advance_kernel(const __grid_constant
     const bool have = threadIdx.x < n_fin;
     bool accepted = false;
     PixelWork w;
-    w.x = 0; w.y = 0; w.mu = 0; w.c2 = 0;
+    w.x = 0; w.y = 0; w.mu = 0; w.c2 = 0; w.have_ray = false;
     if (have) {
         unsigned long long key;
-        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, w.x, w.y, w.mu, w.c2, key);
+        accepted = fuse_slot(P, cta * TILE_PIX + threadIdx.x, w.x, w.y, w.mu, w.c2, key, w.f_ref, w.have_ray);
     }
-    count_frame(P, n_fin, accepted);
     prepare_pixel(P, w, have);
-    emit_pixel(P, w);
+    emit_pixel(P, w, accepted, n_fin);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -431,3 +431,65 @@ def test_sharded_filter_world1(DF, seq640):
         T = seq.T_C_R(i)
         oracle.update(seq.params, frames[0], frames[i], T.q, T.t, d_ref, c_ref, rows=(20, 460), row_stride=8)
     assert depth_agreement(seq.params, d, d_ref, range(20, 460, 8), rtol=1e-6) > 0.9999
+
+
+def test_deferred_fusion_equals_immediate_fusion(DF, seq640):
+    """The fusion of update k normally runs inside update k+1's first kernel (advance_kernel, straight from registers).
+    Flushing after every update (setup_kernel + fuse_kernel from the maps) and the debug-plane mode must give the same
+    bits, the same counters, and match the oracle."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    n = seq.n_frames - 1  # 5 updates
+    res = []
+    for mode in ("deferred", "flushed", "flags"):
+        f = DF(p)
+        f.set_reference(frames[0])
+        f.fill_state(3.0, 3.0)
+        f.enable_flags(mode == "flags")
+        for i in range(1, n + 1):
+            f.update(frames[i], seq.T_C_R(i))
+            if mode == "flushed":
+                f.flush()
+        d, c = f.download_state()
+        res.append((d, c, f.counters()))
+        f.close()
+    for d, c, cnt in res[1:]:
+        assert np.array_equal(d, res[0][0], equal_nan=True) and np.array_equal(c, res[0][1], equal_nan=True)
+        assert cnt == res[0][2]
+    d_ref, c_ref = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    for i in range(1, n + 1):
+        T = seq.T_C_R(i)
+        oracle.update(p, frames[0], frames[i], T.q, T.t, d_ref, c_ref, rows=(20, 460), row_stride=16)
+    assert depth_agreement(p, res[0][0], d_ref, range(20, 460, 16), rtol=1e-6) > 0.9999
+
+
+def test_accessors_see_the_deferred_fusion(DF, seq640):
+    """Every accessor runs a pending fusion first: counters, masks and a state re-load right after an update."""
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    for i in range(1, 4):
+        f.update(frames[i], seq.T_C_R(i))
+    cnt = f.counters()                      # no explicit flush before
+    assert cnt["frames"] == 3 and cnt["accepted"] > 0 and cnt["active"] >= cnt["accepted"]
+    f.update(frames[4], seq.T_C_R(4))
+    mask = f.variance_mask(1.0)             # reads cov2: must include update 4
+    d, c = f.download_state()
+    assert np.array_equal(mask[20:-20, 20:-20] == 255, ~(c[20:-20, 20:-20] > 1.0))
+    # replacing the state drops back to a full set-up from the maps: same result as a fresh filter
+    f.update(frames[5], seq.T_C_R(5))
+    f.upload_state(d, c)
+    f.update(frames[5], seq.T_C_R(5))
+    d1, c1 = f.download_state()
+    f.close()
+    g = DF(p)
+    g.set_reference(frames[0])
+    g.upload_state(d, c)
+    g.update(frames[5], seq.T_C_R(5))
+    d2, c2 = g.download_state()
+    g.close()
+    assert np.array_equal(d1, d2, equal_nan=True) and np.array_equal(c1, c2, equal_nan=True)
