@@ -20,7 +20,7 @@ h = rows[0]
 ik, iv = h.index("Kernel Name"), h.index("Metric Value")
 per = collections.OrderedDict()
 for r in rows[1:]:
-    name = r[ik].split("(")[0].replace("dmf::", "")
+    name = r[ik].split("(")[0].replace("dmf::", "").replace("void ", "").split("<")[0]
     if name.startswith("render") or "render_kernel" in name:
         continue
     per.setdefault(name, []).append(float(r[iv].replace(",", "")) / 1e3)
