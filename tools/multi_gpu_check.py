@@ -27,6 +27,7 @@ sf.set_reference(frames[0] if rank == 0 else None)
 poses_all = [seq.T_C_R(i) for i in range(n)]
 for rep in range(2):
     sf.fill_state(3.0, 3.0)
+    sf.counters(reset=True)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     poses = sf.broadcast_poses(poses_all if rank == 0 else None)

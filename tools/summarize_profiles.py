@@ -21,7 +21,7 @@ ik, iv = h.index("Kernel Name"), h.index("Metric Value")
 per = collections.OrderedDict()
 for r in rows[1:]:
     name = r[ik].split("(")[0].replace("dmf::", "").replace("void ", "").split("<")[0]
-    if name.startswith("render") or "render_kernel" in name:
+    if not name or "render_kernel" in r[ik]:
         continue
     per.setdefault(name, []).append(float(r[iv].replace(",", "")) / 1e3)
 (PROF / f"{tag}_launches_hd1080_60frames.csv").write_text(src.read_text())
