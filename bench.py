@@ -288,7 +288,7 @@ def ours(args) -> dict | None:
         frames, pitch = None, (w + 15) // 16 * 16
     poses_all = [seq.T_C_R(i) for i in range(F)]
 
-    sf = ShardedDepthFilter(p, device=local_rank, layout=args.layout, block_rows=args.block_rows)
+    sf = ShardedDepthFilter(p, device=local_rank, layout=args.layout, block_rows=args.block_rows, n_ring=args.ring)
     sf.set_reference(frames[0] if rank == 0 else None)
     ctx_stream = sf.ctx_stream
 
@@ -301,8 +301,16 @@ def ours(args) -> dict | None:
         """One full sequence; everything asynchronous."""
         sf.fill_state(3.0, 3.0)
         poses = sf.broadcast_poses(poses_all if rank == 0 else None) if world > 1 else [(T.q, T.t) for T in poses_all]
+        if world > 1:
+            # the frame of update i+1 is announced before update i is launched: its broadcast runs one update early
+            sf.prefetch(frames[1] if rank == 0 else None)
+            for i in range(1, F):
+                if i + 1 < F:
+                    sf.prefetch(frames[i + 1] if rank == 0 else None)
+                sf.update(None, poses[i])
+            return sf.gather_state()
         for i in range(1, F):
-            sf.update(frames[i] if rank == 0 else None, poses[i])
+            sf.update(frames[i], poses[i])
         if world > 1:
             return sf.gather_state()
         sf.flush()  # the deferred fusion of the last update belongs to this step
@@ -483,8 +491,11 @@ def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, pos
     def step():
         sf.fill_state(3.0, 3.0)
         poses = sf.broadcast_poses(poses_all if rank == 0 else None)
+        sf.prefetch_host(host[1] if rank == 0 else None)
         for i in range(1, F):
-            sf.update_host(host[i] if rank == 0 else None, poses[i])
+            if i + 1 < F:
+                sf.prefetch_host(host[i + 1] if rank == 0 else None)
+            sf.update_host(None, poses[i])
         res = sf.gather_state()
         if rank == 0:
             out_d.copy_(res[0], non_blocking=True)
@@ -549,6 +560,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU-baseline sample (default: host cores)")
     ap.add_argument("--layout", default="cyclic", choices=["cyclic", "bands"], help="row ownership for N > 1")
     ap.add_argument("--block-rows", type=int, default=8, help="rows per block of the cyclic layout")
+    ap.add_argument("--ring", type=int, default=3, help="frames in flight per rank for N > 1 (broadcast ring depth)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-port", action="store_true", help="--impl reference: use the oracle port even at 640x480")

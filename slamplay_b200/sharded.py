@@ -83,6 +83,7 @@ class ShardedDepthFilter:
         self.H, self.W = params.height, params.width
         self._k = 0
         self._ring_events = [None] * n_ring
+        self._queue = []  # frames announced with prefetch() / prefetch_host(), oldest first: (buffer, comm stream, ring slot)
         self._attach(device, n_ring)
 
     # The three hooks below are the only places that touch CUDA; tests/test_sharded_gloo.py
@@ -99,6 +100,8 @@ class ShardedDepthFilter:
         self.tdev = dev
         self.ring = [torch.empty((self.H, self.pitch), dtype=torch.uint8, device=dev) for _ in range(n_ring)]
         self.comm_stream = torch.cuda.Stream(device=dev)
+        # one side stream per ring slot: an update waits for ITS frame only, not for frames announced later
+        self.comm_streams = [self.comm_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_ring - 1)]
         self.ctx_stream = torch.cuda.ExternalStream(self.filter.stream(), device=dev)
         d_ptr, c_ptr, pitch = self.filter.device_state()
         assert pitch == self.W * 8
@@ -109,9 +112,10 @@ class ShardedDepthFilter:
         self.filter.set_reference_device(buf.data_ptr(), self.pitch)
         self.filter.sync()
 
-    def _launch(self, buf, pose, after_comm: bool) -> None:
+    def _launch(self, buf, pose, after_comm) -> None:
+        """after_comm: the CUDA stream whose queued work produces `buf` (None / False: the frame is complete)."""
         self.filter.update_device(buf.data_ptr(), self.pitch, pose,
-                                  wait_stream=self.comm_stream.cuda_stream if after_comm else None)
+                                  wait_stream=after_comm.cuda_stream if after_comm else None)
 
     # -- setup ---------------------------------------------------------------------------
     def set_reference(self, ref_dev) -> None:
@@ -145,48 +149,70 @@ class ShardedDepthFilter:
         return [(tuple(r[:4]), tuple(r[4:])) for r in host]
 
     # -- per frame -------------------------------------------------------------------------
-    def update(self, frame_dev, pose: Tuple[tuple, tuple]) -> None:
-        """frame_dev: torch uint8 (H, pitch) tensor on rank 0 (ignored elsewhere).  Asynchronous:
-        the broadcast runs on a side stream, double-buffered against the previous frame's kernel."""
+    def _move_frame(self, frame_dev, host_frame) -> None:
+        """Enqueue the transfer of one frame to every rank (rank 0: optional H2D copy, then NCCL broadcast on a side
+        stream) into the next ring slot and remember it for the update that will consume it."""
         torch, dist = self.torch, self.dist
-        if self.world == 1:
-            self._launch(frame_dev, pose, False)
-            return
         b = self._k % len(self.ring)
         self._k += 1
-        buf = frame_dev if self.rank == 0 else self.ring[b]
+        buf = self.ring[b] if (self.rank != 0 or host_frame is not None) else frame_dev
         if self.tdev.type != "cuda":  # gloo / CPU protocol test: synchronous
-            dist.broadcast(buf, src=0, group=self.group)
-            self._launch(buf, pose, False)
+            if self.rank == 0 and host_frame is not None:
+                buf[:, : self.W].copy_(host_frame)
+            if self.world > 1:
+                dist.broadcast(buf, src=0, group=self.group)
+            self._queue.append((buf, None, b))
             return
-        with torch.cuda.stream(self.comm_stream):
+        cs = self.comm_streams[b]
+        with torch.cuda.stream(cs):
             if self._ring_events[b] is not None:
-                self.comm_stream.wait_event(self._ring_events[b])  # kernel that last read ring[b] is done
-            dist.broadcast(buf, src=0, group=self.group)
-        self._launch(buf, pose, True)
-        ev = torch.cuda.Event()
-        ev.record(self.ctx_stream)
-        self._ring_events[b] = ev
-
-    def update_host(self, host_frame, pose: Tuple[tuple, tuple]) -> None:
-        """End-to-end form of update(): `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0 (None
-        elsewhere).  Rank 0 copies it to HBM on the side stream, the frame is broadcast, every rank updates
-        its band; all of it overlapped with the previous frame's kernels."""
-        torch, dist = self.torch, self.dist
-        b = self._k % len(self.ring)
-        self._k += 1
-        buf = self.ring[b]
-        with torch.cuda.stream(self.comm_stream):
-            if self._ring_events[b] is not None:
-                self.comm_stream.wait_event(self._ring_events[b])
-            if self.rank == 0:
+                cs.wait_event(self._ring_events[b])  # the kernel that last read ring[b] is done
+            if self.rank == 0 and host_frame is not None:
                 buf[:, : self.W].copy_(host_frame, non_blocking=True)
             if self.world > 1:
                 dist.broadcast(buf, src=0, group=self.group)
-        self._launch(buf, pose, True)
-        ev = torch.cuda.Event()
-        ev.record(self.ctx_stream)
-        self._ring_events[b] = ev
+        self._queue.append((buf, cs, b))
+
+    def _consume(self, pose) -> None:
+        buf, cs, b = self._queue.pop(0)
+        self._launch(buf, pose, cs)
+        if cs is not None:
+            ev = self.torch.cuda.Event()
+            ev.record(self.ctx_stream)
+            self._ring_events[b] = ev
+
+    def prefetch(self, frame_dev) -> None:
+        """Announce the frame of a FUTURE update (frames are consumed in the order they were announced).  Its
+        broadcast is enqueued now, so it can run in a gap one update earlier: ncc_kernel keeps every SM busy with
+        persistent CTAs, and an NCCL kernel enqueued right before the update it feeds would have to wait for the
+        previous ncc_kernel to drain, putting the broadcast and the frame-only precompute on the critical path."""
+        if self.world == 1:
+            self._queue.append((frame_dev, None, 0))
+        else:
+            self._move_frame(frame_dev, None)
+
+    def prefetch_host(self, host_frame) -> None:
+        """prefetch() for the end-to-end path: `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0."""
+        self._move_frame(None, host_frame if self.rank == 0 else None)
+
+    def update(self, frame_dev, pose: Tuple[tuple, tuple]) -> None:
+        """frame_dev: torch uint8 (H, pitch) tensor on rank 0 (ignored elsewhere, and ignored everywhere if frames
+        were announced with prefetch()).  Asynchronous: the broadcast runs on a side stream, multi-buffered against
+        the previous frames' kernels."""
+        if not self._queue:
+            if self.world == 1:
+                self._launch(frame_dev, pose, None)
+                return
+            self._move_frame(frame_dev, None)
+        self._consume(pose)
+
+    def update_host(self, host_frame, pose: Tuple[tuple, tuple]) -> None:
+        """End-to-end form of update(): `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0 (None
+        elsewhere; ignored if frames were announced with prefetch_host()).  Rank 0 copies it to HBM on the side
+        stream, the frame is broadcast, every rank updates its rows; all of it overlapped with the previous kernels."""
+        if not self._queue:
+            self._move_frame(None, host_frame if self.rank == 0 else None)
+        self._consume(pose)
 
     # -- results ---------------------------------------------------------------------------
     def gather_state(self):

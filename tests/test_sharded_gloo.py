@@ -93,8 +93,16 @@ def _worker(rank, world, port, out_path, layout):
     sf.fill_state(3.0, 3.0)
     poses = sf.broadcast_poses([seq.T_C_R(i) for i in range(seq.n_frames)] if rank == 0 else None)
     assert len(poses) == seq.n_frames
-    for i in range(1, seq.n_frames):
-        sf.update(frames[i] if rank == 0 else None, poses[i])
+    if layout == "cyclic":  # look-ahead form: the next frame is announced before the current update is launched
+        sf.prefetch(frames[1] if rank == 0 else None)
+        for i in range(1, seq.n_frames):
+            if i + 1 < seq.n_frames:
+                sf.prefetch(frames[i + 1] if rank == 0 else None)
+            sf.update(None, poses[i])
+    else:
+        for i in range(1, seq.n_frames):
+            sf.update(frames[i] if rank == 0 else None, poses[i])
+    assert not sf._queue
     res = sf.gather_state()
     cnt = sf.counters()
     if rank == 0:

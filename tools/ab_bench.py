@@ -25,7 +25,9 @@ for lib in libs:
     os.environ["DMF_LIB"] = os.path.abspath(lib)
     _lib._cache.pop("dmf", None)
     try:
-        f = DepthFilter(seq.params, device=0)
+        # DMF_AB_CYCLIC=N: the context of rank 0 of an N-GPU run (1/N of the rows, whole-frame moment table)
+        ncyc = int(os.environ.get("DMF_AB_CYCLIC", "0"))
+        f = DepthFilter(seq.params, device=0, cyclic=(8, ncyc, 0)) if ncyc > 1 else DepthFilter(seq.params, device=0)
         f.set_reference_device(frames[0].data_ptr(), pitch)
         st = torch.cuda.ExternalStream(f.stream())
         best = 1e9
