@@ -115,7 +115,7 @@ class ShardedDepthFilter:
     def _launch(self, buf, pose, after_comm) -> None:
         """after_comm: the CUDA stream whose queued work produces `buf` (None / False: the frame is complete)."""
         self.filter.update_device(buf.data_ptr(), self.pitch, pose,
-                                  wait_stream=after_comm.cuda_stream if after_comm else None)
+                                  wait_stream=after_comm.cuda_stream if after_comm is not None and after_comm is not False else None)
 
     # -- setup ---------------------------------------------------------------------------
     def set_reference(self, ref_dev) -> None:
