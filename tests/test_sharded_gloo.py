@@ -128,3 +128,69 @@ def test_sharded_protocol_world2_gloo(tmp_path, layout):
     out = tmp_path / "result.txt"
     mp.spawn(_worker, args=(2, _free_port(), str(out), layout), nprocs=2, join=True)
     assert out.read_text() == "1 1", "sharded (2 bands) and unsharded results / counters differ"
+
+
+def test_cuda_branch_of_the_frame_pipeline_with_mock_streams(monkeypatch):
+    """The stream / event choreography of prefetch -> update (one side stream per ring slot, ring-slot reuse guarded by
+    the event of the update that last read it) exercised on CPU with recording stand-ins for the CUDA objects."""
+    import contextlib
+    import types
+
+    from slamplay_b200.sharded import ShardedDepthFilter
+    from slamplay_b200.synth import make_sequence
+
+    log = []
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name, self.cuda_stream = name, hash(name) & 0xFFFF
+
+        def wait_event(self, ev):
+            log.append(("wait", self.name, ev.tag))
+
+    class FakeEvent:
+        n = 0
+
+        def __init__(self):
+            FakeEvent.n += 1
+            self.tag = FakeEvent.n
+
+        def record(self, stream):
+            log.append(("record", stream.name, self.tag))
+
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+
+    class MockCuda(ShardedDepthFilter):
+        def _attach(self, device, n_ring):
+            self.tdev = types.SimpleNamespace(type="cuda")
+            self.ring = [torch.zeros((self.H, self.pitch), dtype=torch.uint8) for _ in range(n_ring)]
+            self.comm_streams = [FakeStream(f"comm{i}") for i in range(n_ring)]
+            self.comm_stream = self.comm_streams[0]
+            self.ctx_stream = FakeStream("ctx")
+            self.launched = []
+
+        def _launch(self, buf, pose, after_comm):
+            self.launched.append((int(buf[0, 0]), pose, after_comm.name if after_comm is not None else None))
+
+    seq = make_sequence("tiny", width=192, height=128, n_frames=8)
+    sf = MockCuda(seq.params, n_ring=3)
+    host = [torch.full((sf.H, sf.W), i, dtype=torch.uint8) for i in range(8)]
+    sf.prefetch_host(host[1])
+    for i in range(1, 8):
+        if i + 1 < 8:
+            sf.prefetch_host(host[i + 1])
+        sf.update_host(None, ("q", i))
+    assert not sf._queue
+    # every update got ITS frame, in order, and waited on the side stream of its own ring slot only
+    assert [(f, p[1]) for f, p, _ in sf.launched] == [(i, i) for i in range(1, 8)]
+    assert [s for _, _, s in sf.launched] == [f"comm{(i - 1) % 3}" for i in range(1, 8)]
+    # a ring slot is rewritten only after the event recorded behind the update that last read it
+    waits = [e for e in log if e[0] == "wait"]
+    records = [e for e in log if e[0] == "record"]
+    assert len(records) == 7 and all(r[1] == "ctx" for r in records)
+    assert [w[1] for w in waits] == [f"comm{k % 3}" for k in range(3, 7)]       # frames 4..7 reuse slots 0,1,2,0
+    assert [w[2] for w in waits] == [records[k - 3][2] for k in range(3, 7)]    # ... after updates 1..4
+    # without look-ahead the same calls fall back to transfer-then-launch
+    sf.update_host(host[3], ("q", 99))
+    assert sf.launched[-1][:2] == (3, ("q", 99)) and not sf._queue
