@@ -166,7 +166,9 @@ int dmf_sync(dmf_ctx *ctx);
 
 /*
  * Optional per-kernel timing for the roofline report (bench.py): with timing enabled every update()
- * brackets its four kernels (in launch order: setup, block moments, ncc, fuse) with CUDA events on the context stream.
+ * serialises its kernels on the context stream and brackets them with CUDA events; the four slots are, in launch
+ * order: set-up (advance_kernel = fusion of the previous update + set-up, or setup_kernel), block moments, ncc, and the
+ * stand-alone fusion (only when one runs right after the update: debug planes on).
  * dmf_get_timing synchronises and returns the accumulated milliseconds per kernel class and the number
  * of frames they cover.  Off by default (the events cost ~1 % on small frames).
  */

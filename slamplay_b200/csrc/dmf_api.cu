@@ -22,7 +22,7 @@ struct dmf_ctx_impl {
     int row0 = 0, blk = 1, cyc = 1, ph = 0, n_rows = 0;
     std::vector<std::pair<int, int>> spans;     // owned interior rows as ascending [y0, y1) intervals
     std::vector<std::pair<int, int>> io_spans;  // rows moved by upload / download (spans, plus border rows a contiguous band asked for)
-    // stream: setup -> ncc -> fuse of every frame; mom_stream: moments_kernel of the NEXT frame runs beside them
+    // stream: advance (fusion + set-up) -> ncc of every update; mom_stream: moments_kernel of the NEXT update runs beside them
     cudaStream_t stream = nullptr, copy_stream = nullptr, mom_stream = nullptr;
     // images
     uint8_t *d_ref = nullptr;
@@ -39,7 +39,7 @@ struct dmf_ctx_impl {
     int *d_dbg_n = nullptr;
     unsigned long long *d_counters = nullptr;  // 3 counters + eval (sum_sq as double bits, count)
     double *d_eval = nullptr;                  // [0] = sum_sq ; count lives in d_counters[3]
-    // per-frame scratch of the three-kernel update (setup -> ncc -> fuse)
+    // per-update scratch of the advance / setup -> ncc -> fuse pipeline
     // slot-indexed scratch, double-buffered by update parity (advance_kernel reads update k's while writing k+1's)
     dmf::PixelRec *d_rec[2] = {nullptr, nullptr};            // n_pix 64-byte records
     unsigned long long *d_best[2] = {nullptr, nullptr};
@@ -63,7 +63,7 @@ struct dmf_ctx_impl {
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
-    // optional per-kernel timing (dmf_set_timing): 5 events per frame bracket the 4 kernels
+    // optional per-kernel timing (dmf_set_timing): 5 events per update bracket the 4 timing slots
     bool timing_on = false;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -355,7 +355,7 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
     CUX(cudaMemsetAsync(c->d_depth, 0, W * H * sizeof(double), c->stream));
     CUX(cudaMemsetAsync(c->d_cov2, 0, W * H * sizeof(double), c->stream));
     {
-        // scratch of the setup -> ncc -> fuse pipeline
+        // scratch of the advance / setup -> ncc -> fuse pipeline
         c->n_pix = (int)((W - 2 * (size_t)params->border) * (size_t)c->n_rows);
         c->tiles_x = (int)((W - 2 * (size_t)params->border + dmf::TILE_W - 1) / dmf::TILE_W);
         c->n_bands = (c->n_rows + dmf::TILE_H - 1) / dmf::TILE_H;

@@ -6,24 +6,27 @@
 //   getBilinearInterpolatedValue ref:165-174, updateDepthFilter ref:482-567.
 //
 // Once per reference frame: ref_stats_kernel (patch sums) and ref_expand_kernel (7-byte rows as aligned 64-bit words).
-// Per frame four kernels run back to back on the context stream:
+// Per update three kernels run; the fusion of update k is deferred into the set-up of update k+1:
 //
-//   setup_kernel   (thread = pixel, FP64)  gate ref:366, projections of mu and mu±3σ ref:402-422,
-//                 trip count n of the l-loop ref:432.  The n samples of a pixel are cut into
-//                 work UNITS of at most CHUNK consecutive samples; units are appended to
-//                 per-length lists in HBM (length CHUNK first, ..., length 1 last).
-//   moments_kernel (thread = column, sliding 7-row window)  the frame-only integer moments of every
-//                 8x8 block position (see "NCC arithmetic"), for the row groups some sample reads; as a
-//                 by-product the "expanded" frame: the 8 bytes [x, x+8) of every row position as one aligned
-//                 64-bit word, so that a sample fetches each row of its 8x8 block with one LDG.64.
+//   advance_kernel (thread = slot of the previous update, FP64)  accept test ref:443, triangulation, uncertainty and
+//                 Gaussian fusion ref:482-567 of update k-1, in place on the HBM-resident maps; then, straight from
+//                 the fused registers, the set-up of update k: gate ref:366, projections of mu and mu±3σ ref:402-422,
+//                 trip count n of the l-loop ref:432.  The n samples of a pixel are cut into work UNITS of at most
+//                 CHUNK consecutive samples; units are appended to per-length lists in HBM (length CHUNK first, ...,
+//                 length 1 last).  Active pixels live in SLOTS: every 32x8 tile keeps its active pixels packed at the
+//                 front of its own slot range.  setup_kernel (thread = pixel, state from the maps) and fuse_kernel
+//                 (thread = slot) are the two halves as stand-alone kernels: first update after the maps were
+//                 loaded, strict drop-in mode, debug planes, and whenever the maps are read (flush).
+//   moments_kernel (thread = column, sliding 7-row window)  the frame-only integer moments of every 8x8 block
+//                 position (see "NCC arithmetic"); as a by-product the "expanded" frame: the 8 bytes [x, x+8) of
+//                 every row position as one aligned 64-bit word, so that a sample fetches each row of its 8x8 block
+//                 with one LDG.64.  Runs on its own stream beside the previous update (double-buffered tables).
 //   ncc_kernel     (thread = unit)  persistent CTAs pull 64-unit grabs of the lists with an
 //                 atomic cursor, so every warp runs units of ONE length (no divergence on the
 //                 search length, which varies 0..286 per pixel) and the chip stays balanced
 //                 whatever the spatial distribution of converged / diverged pixels.  The unit's
 //                 7x7 reference patch lives in registers for all its samples; its best sample
-//                 goes to the pixel's 64-bit arg-max key with one atomicMax.
-//   fuse_kernel    (thread = pixel, FP64)  accept test ref:443, triangulation, uncertainty and
-//                 Gaussian fusion ref:482-567, in place on the HBM-resident maps.
+//                 goes to the slot's 64-bit arg-max key with one atomicMax.
 //
 // NCC arithmetic.  All 49 taps of one NCC share the same four bilinear weights (the tap
 // offsets are integers, ref:461), so every sum the ZNCC needs is a linear / quadratic form

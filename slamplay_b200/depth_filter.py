@@ -180,7 +180,8 @@ class DepthFilter:
         self._ck(self._lib.dmf_set_timing(self._ctx, int(on)), "dmf_set_timing")
 
     def timing(self, reset: bool = False) -> dict:
-        """Accumulated per-kernel milliseconds {moments, setup, ncc, fuse} and the frames they cover."""
+        """Accumulated per-kernel milliseconds and the frames they cover: setup_ms = advance_kernel (fusion of the previous
+        update + set-up) or setup_kernel, moments_ms, ncc_ms, fuse_ms = stand-alone fusion behind the update (debug planes)."""
         ms = (C.c_double * 4)()
         n = C.c_uint64()
         self._ck(self._lib.dmf_get_timing(self._ctx, ms, C.byref(n), int(reset)), "dmf_get_timing")
