@@ -422,6 +422,13 @@ def ours(args) -> dict | None:
     if world > 1:
         dist.barrier()
 
+    # ---- N > 1: the gathered maps must be bit-identical to a single-GPU run (ref:366,546-564: pixels are independent)
+    if world > 1 and not args.no_parity:
+        gathered = one_step()
+        if rank == 0:
+            result["parity_sample"] = multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, local_rank)
+        dist.barrier()
+
     # ---- CPU baseline (rank 0, N == 1 only) + parity on the sampled rows -------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -518,6 +525,32 @@ def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, pos
             "ms_per_step": dt * 1e3, "api": "ShardedDepthFilter.update_host (pinned host frames on rank 0, NCCL broadcast) + gather_state + D2H"}
 
 
+def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_index) -> dict:
+    """Rank 0: the same sequence on ONE context; SHA-256 and bitwise comparison with the maps gathered from N ranks."""
+    import hashlib
+
+    from slamplay_b200.depth_filter import DepthFilter
+
+    h, w = seq.shape
+    multi = [t.cpu().numpy().copy() for t in gathered]
+    f = DepthFilter(seq.params, device=device_index)
+    f.set_reference_device(frames[0].data_ptr(), pitch)
+    f.fill_state(3.0, 3.0)
+    s = torch.cuda.current_stream().cuda_stream
+    for i in range(1, seq.n_frames):
+        f.update_device(frames[i].data_ptr(), pitch, poses_all[i], wait_stream=s)
+    single = f.download_state()
+    f.close()
+    b = seq.params.border
+    I = (slice(b, h - b), slice(b, w - b))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    same = [float((m[I].view(np.int64) == s1[I].view(np.int64)).mean()) for m, s1 in zip(multi, single)]
+    return {"against": "the same sequence on one GPU (rank 0), all interior pixels",
+            "sha256_depth": sha(multi[0][I]), "sha256_depth_1gpu": sha(single[0][I]),
+            "sha256_cov2": sha(multi[1][I]), "sha256_cov2_1gpu": sha(single[1][I]),
+            "bit_identical": bool(same[0] == 1.0 and same[1] == 1.0), "bitwise_equal_frac": {"depth": same[0], "cov2": same[1]}}
+
+
 def cpu_baseline_and_parity(args, seq, frames, sf, torch) -> dict:
     import oracle
 
@@ -563,6 +596,7 @@ def main():
     ap.add_argument("--ring", type=int, default=3, help="frames in flight per rank for N > 1 (broadcast ring depth)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bitwise comparison with a single-GPU run")
     ap.add_argument("--force-port", action="store_true", help="--impl reference: use the oracle port even at 640x480")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

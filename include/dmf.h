@@ -226,6 +226,46 @@ int dmf_variance_mask(dmf_ctx *ctx, double max_variance, uint8_t *mask_host, siz
 int dmf_point_cloud(dmf_ctx *ctx, const uint8_t *color_host, size_t color_step, int channels, double max_variance,
                     float *xyz_host, uint8_t *rgb_host, uint64_t capacity, uint64_t *n_points);
 
+/*
+ * Multi-GPU frame distribution on the copy engines (every rank needs the whole current frame).
+ * One PRODUCER process (the rank that receives the frames) owns a ring of `n_slots` frames in its device memory;
+ * every rank, the producer's included, opens the ring as CONSUMER number 0 .. n_consumers-1 from the 192-byte handle
+ * (plain bytes: send them with any transport).  dmf_ring_publish enqueues the copy of one frame (pinned host memory or
+ * device memory, `step` bytes per row) into the next slot; dmf_update_ring is dmf_update() against the next frame of
+ * the ring: the context's copy stream waits for the slot, pulls it over NVLink peer-to-peer (or locally) with a copy
+ * engine into the context's own buffer, releases the slot and launches the kernels.  All of it is stream-ordered
+ * (cuStreamWaitValue32 / cuStreamWriteValue32 on a shared flag page): no host ever blocks on another, no SM is used
+ * for the transfer, and frames are consumed in publication order by every consumer.  A consumer that never calls
+ * dmf_update_ring stalls the producer after n_slots frames.
+ */
+#define DMF_RING_HANDLE_BYTES 192
+typedef struct dmf_ring dmf_ring;
+int dmf_ring_create(int device, int n_slots, int width, int height, int n_consumers, dmf_ring **out, uint8_t *handle_out);
+int dmf_ring_open(int device, const uint8_t *handle, int consumer, dmf_ring **out);
+void dmf_ring_close(dmf_ring *ring);
+int dmf_ring_info(const dmf_ring *ring, int *n_slots, int *n_consumers, uint32_t *next_frame);
+int dmf_ring_publish(dmf_ring *ring, const uint8_t *frame, size_t step, void *wait_stream);
+int dmf_update_ring(dmf_ctx *ctx, dmf_ring *ring, const double q_xyzw[4], const double t_xyz[3]);
+
+/*
+ * Measured issue rates of the pipes the kernels of this path run on (the path is bound by instruction
+ * issue and L1/TEX throughput; MEASURED_PEAKS.json holds HBM and bf16 only).  Micro-benchmarks, ~20 ms in total:
+ * thread-operations per clock per SM (from clock64 of the slowest CTA), per second (CUDA events) and the SM clock the
+ * two imply.  ldg64_l1 / ldg128_l1: coalesced loads that hit L1 — one warp-wide LDG.64 is 2 wavefronts of 128 bytes,
+ * one LDG.128 is 4, so wavefronts/clk/SM = per_clk_sm / 32 * {2, 4}.  bench.py uses these as roofline denominators.
+ */
+typedef struct dmf_pipe_rate {
+    double per_clk_sm;   /* thread-ops / clock / SM */
+    double per_second;   /* thread-ops / s, whole chip */
+    double eff_mhz;      /* SM clock during the measurement */
+} dmf_pipe_rate;
+typedef struct dmf_pipe_peaks_t {
+    int32_t n_sm;
+    int32_t reserved;
+    dmf_pipe_rate ffma, dfma, idp4a, i2f_f64, ldg64_l1, ldg128_l1;
+} dmf_pipe_peaks_t;
+int dmf_pipe_peaks(int device, dmf_pipe_peaks_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ def lib() -> C.CDLL:
         L.dmo_update.argtypes = [_P(Params), _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double),
                                  _vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
                                  _P(Counters), _vp, C.c_size_t, _vp, _vp]
+        L.dmo_update_ex.argtypes = [_P(Params), _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double),
+                                    _vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    _P(Counters), _vp, C.c_size_t, _vp, _vp]
         L.dmo_bilinear.restype = C.c_double
         L.dmo_bilinear.argtypes = [_vp, C.c_size_t, C.c_double, C.c_double]
         L.dmo_ncc.restype = C.c_double
@@ -145,6 +148,21 @@ def update(params, ref: np.ndarray, curr: np.ndarray, q, t, depth: np.ndarray, c
                           dbg_n.ctypes.data if dbg_n is not None else None)
     if rc != 0:
         raise RuntimeError("dmo_update failed")
+
+
+def update_ex(params, ref, curr, q, t, depth, cov2, *, rows=None, row_stride=1, counters=None, flags=None,
+              dbg_k=None, dbg_ncc64=None) -> None:
+    """update() plus the diagnostic planes of dmo_update_ex (trip count << 16 | winning iteration; best NCC as f64)."""
+    p = to_params(params)
+    r0, r1 = rows if rows is not None else (0, p.height)
+    rc = lib().dmo_update_ex(C.byref(p), ref.ctypes.data, ref.strides[0], curr.ctypes.data, curr.strides[0], _d4(q), _d3(t),
+                             depth.ctypes.data, depth.strides[0], cov2.ctypes.data, cov2.strides[0], r0, r1, row_stride,
+                             C.byref(counters) if counters is not None else None,
+                             flags.ctypes.data if flags is not None else None, flags.strides[0] if flags is not None else 0,
+                             dbg_k.ctypes.data if dbg_k is not None else None,
+                             dbg_ncc64.ctypes.data if dbg_ncc64 is not None else None)
+    if rc != 0:
+        raise RuntimeError("dmo_update_ex failed")
 
 
 def ref_update(ref: np.ndarray, curr: np.ndarray, q, t, depth: np.ndarray, cov2: np.ndarray) -> None:

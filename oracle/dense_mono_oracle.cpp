@@ -369,7 +369,7 @@ void update_rows(const Cam &c, const Img8 &ref, const Img8 &curr, const SE3 &T,
                  double *depth, size_t dstep, double *cov2, size_t cstep,
                  int row_begin, int row_end, int row_stride,
                  dmf_counters *counters, uint8_t *flags, size_t fstep,
-                 float *dbg_ncc, int32_t *dbg_n, size_t dbg_w) {
+                 float *dbg_ncc, int32_t *dbg_n, size_t dbg_w, int32_t *dbg_k = nullptr, double *dbg_ncc64 = nullptr) {
     int y0 = row_begin < c.border ? c.border : row_begin;
     int y1 = row_end > c.height - c.border ? c.height - c.border : row_end;
     if (row_stride < 1) row_stride = 1;
@@ -401,6 +401,8 @@ void update_rows(const Cam &c, const Img8 &ref, const Img8 &curr, const SE3 &T,
                 evals += (unsigned long long)s.n_eval;
                 if (dbg_ncc) dbg_ncc[size_t(y) * dbg_w + x] = (float)s.best_ncc;
                 if (dbg_n) dbg_n[size_t(y) * dbg_w + x] = s.n_eval;
+                if (dbg_k) dbg_k[size_t(y) * dbg_w + x] = (s.n_steps << 16) | (s.best_step < 0 ? 0xFFFF : s.best_step);
+                if (dbg_ncc64) dbg_ncc64[size_t(y) * dbg_w + x] = s.best_ncc;
                 if (s.ok) {
                     fl |= 2;
                     accepted++;
@@ -467,6 +469,21 @@ int dmo_update(const dmf_params *p, const uint8_t *ref, size_t ref_step, const u
     else
         update_rows<false>(c, r, cu, T, depth, depth_step, cov2, cov2_step, row_begin, row_end, row_stride, counters,
                            flags, flags_step, dbg_ncc, dbg_n, size_t(p->width));
+    return 0;
+}
+
+// dmo_update with two more optional full-image planes (tools/parity_diag.py): dbg_k = (trip count of the loop
+// ref:432 << 16) | index of the winning iteration (0xFFFF: none) — the layout of dmf_download_debug — and the
+// best NCC as a double.
+int dmo_update_ex(const dmf_params *p, const uint8_t *ref, size_t ref_step, const uint8_t *curr, size_t curr_step,
+                  const double q_xyzw[4], const double t_xyz[3], double *depth, size_t depth_step,
+                  double *cov2, size_t cov2_step, int row_begin, int row_end, int row_stride,
+                  dmf_counters *counters, uint8_t *flags, size_t flags_step, int32_t *dbg_k, double *dbg_ncc64) {
+    if (!p || !ref || !curr || !depth || !cov2 || !q_xyzw || !t_xyz || p->ncc_half != 3) return -1;
+    Cam c = make_cam(*p);
+    Img8 r{ref, ref_step}, cu{curr, curr_step};
+    update_rows<false>(c, r, cu, make_se3(q_xyzw, t_xyz), depth, depth_step, cov2, cov2_step, row_begin, row_end, row_stride,
+                       counters, flags, flags_step, nullptr, nullptr, size_t(p->width), dbg_k, dbg_ncc64);
     return 0;
 }
 

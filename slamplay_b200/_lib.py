@@ -38,6 +38,22 @@ class DmfCounters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class DmfPipeRate(C.Structure):
+    _fields_ = [("per_clk_sm", C.c_double), ("per_second", C.c_double), ("eff_mhz", C.c_double)]
+
+
+class DmfPipePeaks(C.Structure):
+    _fields_ = [("n_sm", C.c_int32), ("reserved", C.c_int32), ("ffma", DmfPipeRate), ("dfma", DmfPipeRate),
+                ("idp4a", DmfPipeRate), ("i2f_f64", DmfPipeRate), ("ldg64_l1", DmfPipeRate), ("ldg128_l1", DmfPipeRate)]
+
+    def as_dict(self) -> dict:
+        out = {"n_sm": int(self.n_sm)}
+        for k in ("ffma", "dfma", "idp4a", "i2f_f64", "ldg64_l1", "ldg128_l1"):
+            r = getattr(self, k)
+            out[k] = {"per_clk_sm": r.per_clk_sm, "per_second": r.per_second, "eff_mhz": r.eff_mhz}
+        return out
+
+
 class SynthScene(C.Structure):
     _fields_ = [("plane_z", C.c_double), ("relief_amp", C.c_double), ("relief_period", C.c_double),
                 ("tex_base", C.c_double), ("tex_octaves", C.c_int32), ("seed", C.c_uint32),
@@ -85,6 +101,13 @@ DMF_SYMBOLS = {
     "dmf_set_truth": (C.c_int, [_vp, _vp, C.c_size_t]),
     "dmf_evaluate_depth": (C.c_int, [_vp, C.c_double, _P(C.c_double), _P(C.c_uint64)]),
     "dmf_variance_mask": (C.c_int, [_vp, C.c_double, _vp, C.c_size_t]),
+    "dmf_ring_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(_vp), _vp]),
+    "dmf_ring_open": (C.c_int, [C.c_int, _vp, C.c_int, _P(_vp)]),
+    "dmf_ring_close": (None, [_vp]),
+    "dmf_ring_info": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int), _P(C.c_uint32)]),
+    "dmf_ring_publish": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "dmf_update_ring": (C.c_int, [_vp, _vp, _P(C.c_double), _P(C.c_double)]),
+    "dmf_pipe_peaks": (C.c_int, [C.c_int, _P(DmfPipePeaks)]),
     "dmf_point_cloud": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_double, _vp, _vp, C.c_uint64, _P(C.c_uint64)]),
 }
 SYNTH_DEVICE_SYMBOLS = {

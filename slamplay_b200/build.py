@@ -54,7 +54,7 @@ def _stale(target: Path, sources: list[Path]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     """libdmf.so = C ABI (include/dmf.h) + kernels + the device-side synthetic renderer."""
     target = PKG / "libdmf.so"
-    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "synth.cu", CSRC / "synth_scene.h",
+    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "synth.cu", CSRC / "synth_scene.h", CSRC / "microbench.cu", CSRC / "frame_ring.cu", CSRC / "dmf_internal.h",
             ROOT / "include" / "dmf.h", ROOT / "include" / "dmf_synth.h"]
     if not force and not _stale(target, srcs):
         return target
@@ -66,7 +66,10 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     out1 = _run([nvcc, *NVCC_FLAGS, *extra, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")], build / "dmf_api.ptxas.log")
     # the renderer must not contract a*b+c into FMA (bit-identical with the g++ build)
     out2 = _run([nvcc, *NVCC_FLAGS, *ccbin, "-fmad=false", "-c", str(CSRC / "synth.cu"), "-o", str(build / "synth.o")], build / "synth.ptxas.log")
-    _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "synth.o"), "-lcudart"])
+    _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "microbench.cu"), "-o", str(build / "microbench.o")], build / "microbench.ptxas.log")
+    _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "frame_ring.cu"), "-o", str(build / "frame_ring.o")], build / "frame_ring.ptxas.log")
+    _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "synth.o"), str(build / "microbench.o"),
+          str(build / "frame_ring.o"), "-lcudart", "-lrt"])
     if verbose:
         print(out1)
         print(out2)

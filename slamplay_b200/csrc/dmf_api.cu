@@ -2,6 +2,7 @@
 // Host-side logic only: context, HBM-resident state, double-buffered frame upload,
 // pose inversion (Sophus SE3::inverse, used at ref:491), launches.
 #include "../../include/dmf.h"
+#include "dmf_internal.h"
 #include "dmf_kernels.cuh"
 
 #include <cmath>
@@ -114,7 +115,6 @@ int check_params(const dmf_params *p, std::string &why) {
     if (p->border < 13 || 2 * p->border >= p->width || 2 * p->border >= p->height) { why = "border must be >= 13 (the moment table covers block positions x <= width-16, y <= height-9) and < min(width,height)/2"; return -1; }
     // the arg-max key holds sample indices < 510 (KEY_IDX_BITS = 9); the work-unit encoding chunk indices < 64
     if (!(p->step > 0) || !(p->max_half_len >= 0) || !(p->max_half_len / p->step <= 250.0)) { why = "step must be > 0 and max_half_len/step <= 250"; return -1; }
-    if ((long long)(p->width - 2 * p->border) * (p->height - 2 * p->border) >= (1ll << 26)) { why = "more than 2^26 interior pixels"; return -1; }
     if (!(p->fx != 0) || !(p->fy != 0)) { why = "fx, fy must be non-zero"; return -1; }
     if (!(p->min_cov < p->max_cov)) { why = "min_cov must be < max_cov"; return -1; }
     return 0;
@@ -239,6 +239,29 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
 
 struct dmf_ctx : dmf_ctx_impl {};
 
+void dmf_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+
+int dmf_internal_stage_begin(dmf_ctx *c, int width, int height, dmf_internal_stage *st) {
+    if (!c || !st) return fail(c, DMF_ERR_INVALID, "stage: NULL argument");
+    if (!c->have_ref) return fail(c, DMF_ERR_STATE, "dmf_update_ring: dmf_set_reference() has not been called");
+    if (width != c->prm.width || height != c->prm.height) return fail(c, DMF_ERR_INVALID, "dmf_update_ring: the ring's frame size differs from the context's");
+    CU(cudaSetDevice(c->device));
+    const int b = (int)(c->frame_idx & 1);
+    c->frame_idx++;
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    st->copy_stream = (void *)c->copy_stream;
+    st->dst = c->d_curr[b];
+    st->pitch = c->img_pitch;
+    st->buffer = b;
+    return DMF_OK;
+}
+
+int dmf_internal_stage_launch(dmf_ctx *c, const dmf_internal_stage *st, const double q[4], const double t[3]) {
+    const int b = st->buffer;
+    CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    return launch_update(c, c->d_curr[b], c->img_pitch, q, t, c->ev_copied[b], c->ev_consumed[b]);
+}
+
 extern "C" {
 
 int dmf_abi_version(void) { return DMF_ABI_VERSION; }
@@ -362,6 +385,12 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         if (c->n_bands < 1) c->n_bands = 1;
         c->n_ctas = c->tiles_x * c->n_bands;
         c->n_slots = c->n_ctas * dmf::TILE_PIX;  // >= n_pix (edge tiles are partly empty)
+        // work units are (slot << CHUNK_BITS) | chunk in 32 bits: the slot index (not the pixel count) must fit 26 bits
+        if ((long long)c->n_ctas * dmf::TILE_PIX > (1ll << (32 - dmf::CHUNK_BITS))) {
+            int rc_ = fail(nullptr, DMF_ERR_INVALID, "dmf_create: the rows of this context need more than 2^26 pixel slots (split the image into more contexts)");
+            dmf_destroy(ctx);
+            return rc_;
+        }
         const size_t np = (size_t)c->n_slots;
         const int n_max = (int)(2.0 * params->max_half_len / params->step) + 2;  // trip-count bound of ref:432
         const size_t max_full = (size_t)(n_max / dmf::CHUNK) + 1;

@@ -163,6 +163,12 @@ class DepthFilter:
         self._ck(self._lib.dmf_update_device(self._ctx, C.c_void_p(dev_ptr), step, q, t,
                                              C.c_void_p(wait_stream) if wait_stream else None), "dmf_update_device")
 
+    def update_ring(self, ring, T_C_R) -> None:
+        """update() against the next frame of a FrameRing (dmf_update_ring): the frame is pulled into this context's
+        buffer by a copy engine, ordered against the producer by stream memory operations; asynchronous."""
+        q, t = _pose_arrays(T_C_R)
+        self._ck(self._lib.dmf_update_ring(self._ctx, ring._ptr, q, t), "dmf_update_ring")
+
     def flush(self) -> None:
         """Enqueue the deferred fusion of the last update (asynchronous); every accessor does this implicitly."""
         self._ck(self._lib.dmf_flush(self._ctx), "dmf_flush")

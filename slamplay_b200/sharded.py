@@ -62,11 +62,15 @@ class _DevArray:
 class ShardedDepthFilter:
     """Depth filter whose state is split into row bands over the ranks of a process group."""
 
-    def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 3,
-                 layout: str = "cyclic", block_rows: int = 8):
+    def __init__(self, params, *, group=None, device: Optional[int] = None, n_ring: int = 4,
+                 layout: str = "cyclic", block_rows: int = 8, transport: str = "auto"):
         """layout "cyclic" (default): blocks of `block_rows` interior rows dealt round-robin to the ranks —
         convergence varies smoothly down the image, so this balances the per-rank work; "bands": one
-        contiguous band per rank (SURVEY.md 8e first choice; measured 4x imbalance on the 4K sequence)."""
+        contiguous band per rank (SURVEY.md 8e first choice; measured 4x imbalance on the 4K sequence).
+        transport "ring" (default on CUDA with more than one rank): rank 0 publishes every frame into a ring in its
+        HBM and every rank pulls it with a copy engine over NVLink (frame_ring.py: no SM, no collective kernel);
+        "broadcast": one NCCL / gloo broadcast per frame on a side stream (the CPU protocol test, and the fallback
+        where stream memory operations are unavailable)."""
         import torch
         import torch.distributed as dist
 
@@ -81,10 +85,20 @@ class ShardedDepthFilter:
         self.rows = (r0, r1)
         self.pitch = (params.width + 15) // 16 * 16
         self.H, self.W = params.height, params.width
+        if n_ring < 2:
+            raise ValueError("n_ring must be >= 2: the one-frame look-ahead of prefetch() needs a second ring slot")
         self._k = 0
         self._ring_events = [None] * n_ring
         self._queue = []  # frames announced with prefetch() / prefetch_host(), oldest first: (buffer, comm stream, ring slot)
+        self.n_ring = n_ring
+        self.transport = transport
+        self.frame_ring = self.frame_ring_out = None
+        self._published = self._consumed = 0
         self._attach(device, n_ring)
+        if self.transport == "auto":
+            self.transport = "ring" if (self.world > 1 and getattr(self.tdev, "type", "cpu") == "cuda" and self.filter is not None) else "broadcast"
+        if self.transport == "ring":
+            self._attach_ring()
 
     # The three hooks below are the only places that touch CUDA; tests/test_sharded_gloo.py
     # overrides them with an oracle-backed band on CPU tensors to exercise the protocol
@@ -108,14 +122,47 @@ class ShardedDepthFilter:
         self.depth_t = torch.as_tensor(_DevArray(d_ptr, (self.H, self.W), "<f8"), device=dev)
         self.cov2_t = torch.as_tensor(_DevArray(c_ptr, (self.H, self.W), "<f8"), device=dev)
 
+    def _attach_ring(self) -> None:
+        """Rank 0 creates the frame ring, every rank (rank 0 included) opens it as consumer number `rank`."""
+        from .frame_ring import FrameRing
+        dist = self.dist
+        box = [None]
+        if self.rank == 0:
+            self.frame_ring_out = FrameRing.create(self.device, self.n_ring, self.W, self.H, self.world)
+            box[0] = self.frame_ring_out.handle
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=self.group)
+        self.frame_ring = FrameRing.open(self.device, box[0], self.rank)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _ring_publish(self, frame_dev, host_frame) -> None:
+        if self.rank != 0:
+            return
+        if self._published - self._consumed >= self.n_ring:
+            raise RuntimeError("more frames announced than ring slots: call update() before announcing the next frame")
+        if host_frame is not None:  # pinned host frame: H2D by a copy engine straight into the ring slot
+            self.frame_ring_out.publish(host_frame.data_ptr(), host_frame.stride(0), None)
+        else:
+            self.frame_ring_out.publish(frame_dev.data_ptr(), frame_dev.stride(0), self.torch.cuda.current_stream(self.tdev).cuda_stream)
+        self._published += 1
+
+    def _ring_update(self, frame_dev, host_frame, pose) -> None:
+        if self.rank == 0 and self._published == self._consumed:
+            self._ring_publish(frame_dev, host_frame)
+        self.filter.update_ring(self.frame_ring, pose)
+        self._consumed += 1
+
     def _set_reference(self, buf) -> None:
         self.filter.set_reference_device(buf.data_ptr(), self.pitch)
         self.filter.sync()
 
     def _launch(self, buf, pose, after_comm) -> None:
-        """after_comm: the CUDA stream whose queued work produces `buf` (None / False: the frame is complete)."""
-        self.filter.update_device(buf.data_ptr(), self.pitch, pose,
-                                  wait_stream=after_comm.cuda_stream if after_comm is not None and after_comm is not False else None)
+        """after_comm: the CUDA stream whose queued work produces `buf`; None: torch's current stream (a frame rendered
+        or copied by the caller just before this call is complete once that stream reaches this point)."""
+        if after_comm is None or after_comm is False:
+            after_comm = self.torch.cuda.current_stream(self.tdev)
+        self.filter.update_device(buf.data_ptr(), self.pitch, pose, wait_stream=after_comm.cuda_stream)
 
     # -- setup ---------------------------------------------------------------------------
     def set_reference(self, ref_dev) -> None:
@@ -164,6 +211,7 @@ class ShardedDepthFilter:
             self._queue.append((buf, None, b))
             return
         cs = self.comm_streams[b]
+        cs.wait_stream(torch.cuda.current_stream(self.tdev))  # the caller's stream may still be writing the frame
         with torch.cuda.stream(cs):
             if self._ring_events[b] is not None:
                 cs.wait_event(self._ring_events[b])  # the kernel that last read ring[b] is done
@@ -186,19 +234,26 @@ class ShardedDepthFilter:
         broadcast is enqueued now, so it can run in a gap one update earlier: ncc_kernel keeps every SM busy with
         persistent CTAs, and an NCCL kernel enqueued right before the update it feeds would have to wait for the
         previous ncc_kernel to drain, putting the broadcast and the frame-only precompute on the critical path."""
-        if self.world == 1:
+        if self.transport == "ring":
+            self._ring_publish(frame_dev, None)
+        elif self.world == 1:
             self._queue.append((frame_dev, None, 0))
         else:
             self._move_frame(frame_dev, None)
 
     def prefetch_host(self, host_frame) -> None:
         """prefetch() for the end-to-end path: `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0."""
+        if self.transport == "ring":
+            self._ring_publish(None, host_frame)
+            return
         self._move_frame(None, host_frame if self.rank == 0 else None)
 
     def update(self, frame_dev, pose: Tuple[tuple, tuple]) -> None:
         """frame_dev: torch uint8 (H, pitch) tensor on rank 0 (ignored elsewhere, and ignored everywhere if frames
         were announced with prefetch()).  Asynchronous: the broadcast runs on a side stream, multi-buffered against
         the previous frames' kernels."""
+        if self.transport == "ring":
+            return self._ring_update(frame_dev, None, pose)
         if not self._queue:
             if self.world == 1:
                 self._launch(frame_dev, pose, None)
@@ -210,6 +265,8 @@ class ShardedDepthFilter:
         """End-to-end form of update(): `host_frame` is a pinned torch uint8 (H, W) tensor on rank 0 (None
         elsewhere; ignored if frames were announced with prefetch_host()).  Rank 0 copies it to HBM on the side
         stream, the frame is broadcast, every rank updates its rows; all of it overlapped with the previous kernels."""
+        if self.transport == "ring":
+            return self._ring_update(None, host_frame, pose)
         if not self._queue:
             self._move_frame(None, host_frame if self.rank == 0 else None)
         self._consume(pose)
@@ -273,4 +330,13 @@ class ShardedDepthFilter:
         return out
 
     def close(self) -> None:
-        self.filter.close()
+        if self.filter is not None:
+            self.filter.sync()
+        if self.world > 1 and self.frame_ring is not None:
+            self.dist.barrier(group=self.group)  # nobody unmaps the ring while a peer is still pulling from it
+        for r in (self.frame_ring, self.frame_ring_out):
+            if r is not None:
+                r.close()
+        self.frame_ring = self.frame_ring_out = None
+        if self.filter is not None:
+            self.filter.close()

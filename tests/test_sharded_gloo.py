@@ -148,6 +148,9 @@ def test_cuda_branch_of_the_frame_pipeline_with_mock_streams(monkeypatch):
         def wait_event(self, ev):
             log.append(("wait", self.name, ev.tag))
 
+        def wait_stream(self, other):
+            log.append(("wait_stream", self.name, other.name))
+
     class FakeEvent:
         n = 0
 
@@ -160,10 +163,12 @@ def test_cuda_branch_of_the_frame_pipeline_with_mock_streams(monkeypatch):
 
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: FakeStream("current"))
 
     class MockCuda(ShardedDepthFilter):
         def _attach(self, device, n_ring):
             self.tdev = types.SimpleNamespace(type="cuda")
+            self.filter = None
             self.ring = [torch.zeros((self.H, self.pitch), dtype=torch.uint8) for _ in range(n_ring)]
             self.comm_streams = [FakeStream(f"comm{i}") for i in range(n_ring)]
             self.comm_stream = self.comm_streams[0]
@@ -185,6 +190,8 @@ def test_cuda_branch_of_the_frame_pipeline_with_mock_streams(monkeypatch):
     # every update got ITS frame, in order, and waited on the side stream of its own ring slot only
     assert [(f, p[1]) for f, p, _ in sf.launched] == [(i, i) for i in range(1, 8)]
     assert [s for _, _, s in sf.launched] == [f"comm{(i - 1) % 3}" for i in range(1, 8)]
+    # every transfer is ordered after the caller's stream (the frame may still be in production there)
+    assert [e for e in log if e[0] == "wait_stream"] == [("wait_stream", f"comm{k % 3}", "current") for k in range(7)]
     # a ring slot is rewritten only after the event recorded behind the update that last read it
     waits = [e for e in log if e[0] == "wait"]
     records = [e for e in log if e[0] == "record"]
