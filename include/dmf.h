@@ -221,7 +221,7 @@ int dmf_variance_mask(dmf_ctx *ctx, double max_variance, uint8_t *mask_host, siz
  * `color_host`: the reference colour image (`channels` = 3 BGR as cv::imread gives it, or 1 / 4), full image.
  * Writes up to `capacity` points in the reference's scan order: xyz as 3 floats (PointXYZRGB narrows to
  * float), rgb as 3 bytes (r,g,b).  *n_points receives the number of valid points (may exceed capacity).
- * Contiguous-band contexts only.
+ * A context that owns part of the rows (band or block-cyclic) returns the points of its rows, in scan order.
  */
 int dmf_point_cloud(dmf_ctx *ctx, const uint8_t *color_host, size_t color_step, int channels, double max_variance,
                     float *xyz_host, uint8_t *rgb_host, uint64_t capacity, uint64_t *n_points);

@@ -67,9 +67,20 @@ struct Quaterniond {
     }
 };
 
+// Transform<double,3,Isometry>: 3x3 linear part + translation; T * p = linear * p + translation
 struct Isometry3d {
-    static Isometry3d Identity() { return Isometry3d(); }
+    double m[3][3], t[3];
+    static Isometry3d Identity() {
+        Isometry3d r;
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) r.m[i][j] = (i == j) ? 1.0 : 0.0; r.t[i] = 0.0; }
+        return r;
+    }
+    Vector3d operator*(const Vector3d &p) const {
+        return Vector3d((m[0][0] * p[0] + m[0][1] * p[1]) + m[0][2] * p[2] + t[0], (m[1][0] * p[0] + m[1][1] * p[1]) + m[1][2] * p[2] + t[1],
+                        (m[2][0] * p[0] + m[2][1] * p[1]) + m[2][2] * p[2] + t[2]);
+    }
 };
+template <int N> inline Vec<N> &operator*=(Vec<N> &a, double s) { for (int i = 0; i < N; i++) a.v[i] *= s; return a; }
 
 // ColPivHouseholderQR<Matrix2d>: computeInPlace() + _solve_impl() of Eigen 3.3/3.4, fixed 2x2 real.
 template <typename M> class ColPivHouseholderQR;

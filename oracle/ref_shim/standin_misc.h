@@ -1,5 +1,8 @@
-// Inert stand-ins for PCL and the slamplay utils/ headers that only main() / the viz helpers
-// of dense_mapping/test_monocular_mapping.cpp use.  TEST INFRASTRUCTURE ONLY; from scratch.
+// Stand-ins for PCL's point-cloud container and for the slamplay viz helper that only main() of
+// dense_mapping/test_monocular_mapping.cpp uses.  TEST INFRASTRUCTURE ONLY; from scratch.
+// The reference's OWN headers on the path are NOT stood in for: utils/pointcloud/pointcloud_from_image_depth.h,
+// utils/camera/cam_utils.h, utils/io/messages.h and utils/macros.h are compiled from /root/reference (oracle/Makefile
+// puts $(REF_ROOT)/utils on the include path behind this directory).
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -12,22 +15,13 @@ namespace pcl {
 struct PointXYZRGB { float x, y, z; unsigned char r, g, b; };
 template <typename P> struct PointCloud {
     typedef std::shared_ptr<PointCloud<P>> Ptr;
-    std::vector<P> points; unsigned width = 0, height = 0;
+    std::vector<P> points;
+    unsigned width = 0, height = 0;
+    void clear() { points.clear(); width = 0; height = 0; }
+    size_t size() const { return points.size(); }
 };
 }  // namespace pcl
 
 namespace slamplay {
-struct Intrinsics { double fx, fy, cx, cy; };
-template <typename PointT, typename ScalarT>
-inline void getPointCloudFromImageAndDistance(const cv::Mat &, const cv::Mat &, const cv::Mat &, const Intrinsics &, int,
-                                              const Eigen::Isometry3d &, pcl::PointCloud<PointT> &) {}
 template <typename Cloud> struct PointCloudViz { void start() {} void update(const Cloud &) {} };
 }  // namespace slamplay
-
-#ifndef MSG_ASSERT
-#define MSG_ASSERT(cond, msg) do { if (!(cond)) { std::fprintf(stderr, "assert failed: %s\n", #cond); std::abort(); } } while (0)
-#endif
-#ifndef STR
-#define XSTR(x) #x
-#define STR(x) XSTR(x)
-#endif

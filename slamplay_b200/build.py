@@ -54,7 +54,7 @@ def _stale(target: Path, sources: list[Path]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     """libdmf.so = C ABI (include/dmf.h) + kernels + the device-side synthetic renderer."""
     target = PKG / "libdmf.so"
-    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "synth.cu", CSRC / "synth_scene.h", CSRC / "microbench.cu", CSRC / "frame_ring.cu", CSRC / "dmf_internal.h",
+    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "dmf_geometry.h", CSRC / "synth.cu", CSRC / "synth_scene.h", CSRC / "microbench.cu", CSRC / "frame_ring.cu", CSRC / "dmf_internal.h",
             ROOT / "include" / "dmf.h", ROOT / "include" / "dmf_synth.h"]
     if not force and not _stale(target, srcs):
         return target

@@ -131,7 +131,6 @@ void fill_kparams(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long u) {
     K.step = p.step; K.max_half_len = p.max_half_len; K.min_depth = p.min_depth; K.n_sigma = p.n_sigma;
     K.min_cov = p.min_cov; K.max_cov = p.max_cov;
     K.bd = (double)p.border; K.wd = (double)p.width; K.hd = (double)p.height;
-    K.inv_fx = 1.0 / p.fx; K.inv_fy = 1.0 / p.fy; K.inv_step = 1.0 / p.step;
     K.ref = c->d_ref; K.refx = c->d_refx; K.refstat = c->d_refstat;
     K.depth = c->d_depth; K.cov2 = c->d_cov2; K.flags = c->d_flags; K.dbg_ncc = c->d_dbg_ncc; K.dbg_n = c->d_dbg_n; K.counters = c->d_counters;
     K.ref_pitch = c->img_pitch; K.stat_pitch = p.width; K.state_pitch = p.width;
@@ -154,7 +153,6 @@ void fill_finish(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long f) {
     for (int i = 0; i < 4; ++i) K.qi[i] = c->pend_qi[i];
     for (int i = 0; i < 3; ++i) K.ti[i] = c->pend_ti[i];
     K.ti_norm = c->pend_ti_norm;
-    K.inv_ti_norm = 1.0 / c->pend_ti_norm;
 }
 
 // Runs the fusion of the last update if it is still pending (the maps are about to be read or replaced).
@@ -798,20 +796,23 @@ int dmf_point_cloud(dmf_ctx *c, const uint8_t *color_host, size_t color_step, in
     if (channels != 1 && channels != 3 && channels != 4) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: channels must be 1, 3 or 4");
     const dmf_params &p = c->prm;
     if (color_step < (size_t)p.width * channels) return fail(c, DMF_ERR_INVALID, "dmf_point_cloud: step < width*channels");
-    if (c->cyc != 1) return fail(c, DMF_ERR_STATE, "dmf_point_cloud: needs a context that owns a contiguous band");
     CU(cudaSetDevice(c->device));
     { int rc_ = flush_pending(c); if (rc_) return rc_; }
-    const int y0 = c->row0, n_rows = c->n_rows;
+    const int n_rows = c->n_rows;
     *n_points = 0;
     if (n_rows <= 0) return DMF_OK;
+    std::vector<int> rowlist;  // owned image rows, ascending: the reference's scan order restricted to this context
+    for (const auto &sp : c->spans)
+        for (int y = sp.first; y < sp.second; ++y) rowlist.push_back(y);
     uint8_t *d_color = nullptr, *d_rgb = nullptr;
     float *d_xyz = nullptr;
     unsigned int *d_rows = nullptr;
+    int *d_rowlist = nullptr;
     const size_t cpitch = (size_t)p.width * channels;
     const uint64_t max_pts = (uint64_t)n_rows * (uint64_t)(p.width - 2 * p.border);
     const uint64_t cap = capacity < max_pts ? capacity : max_pts;
     int rc = DMF_OK;
-    auto cleanup = [&]() { cudaFree(d_color); cudaFree(d_rgb); cudaFree(d_xyz); cudaFree(d_rows); };
+    auto cleanup = [&]() { cudaFree(d_color); cudaFree(d_rgb); cudaFree(d_xyz); cudaFree(d_rows); cudaFree(d_rowlist); };
 #define CUP(call)                                                                                          \
     do {                                                                                                   \
         cudaError_t e_ = (call);                                                                           \
@@ -821,12 +822,14 @@ int dmf_point_cloud(dmf_ctx *c, const uint8_t *color_host, size_t color_step, in
     CUP(cudaMalloc(&d_rows, (size_t)(n_rows + 1) * sizeof(unsigned int)));
     CUP(cudaMalloc(&d_xyz, (cap ? cap : 1) * 3 * sizeof(float)));
     CUP(cudaMalloc(&d_rgb, (cap ? cap : 1) * 3));
+    CUP(cudaMalloc(&d_rowlist, (size_t)n_rows * sizeof(int)));
+    CUP(cudaMemcpyAsync(d_rowlist, rowlist.data(), (size_t)n_rows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUP(cudaMemcpy2DAsync(d_color, cpitch, color_host, color_step, cpitch, p.height, cudaMemcpyHostToDevice, c->stream));
-    dmf::cloud_count_kernel<<<n_rows, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, p.width, p.border, p.width - p.border, y0,
+    dmf::cloud_count_kernel<<<n_rows, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, p.width, p.border, p.width - p.border, d_rowlist,
                                                            max_variance, d_rows);
     dmf::cloud_scan_kernel<<<1, 1024, 0, c->stream>>>(d_rows, n_rows);
     dmf::cloud_write_kernel<<<n_rows, 256, 0, c->stream>>>(c->d_depth, c->d_cov2, p.width, d_color, (int)cpitch, channels, p.border,
-                                                           p.width - p.border, y0, max_variance, p.cx, p.cy, p.fx, p.fy, d_rows,
+                                                           p.width - p.border, d_rowlist, max_variance, p.cx, p.cy, p.fx, p.fy, d_rows,
                                                            d_xyz, d_rgb, cap);
     CUP(cudaGetLastError());
     unsigned int total = 0;

@@ -51,6 +51,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dmf_geometry.h"
+
 namespace dmf {
 
 constexpr int TILE_W = 32;
@@ -114,12 +116,10 @@ struct KParams {
     int write_flags;
     double ncc_thresh;
     double fx, fy, cx, cy;
-    double inv_fx, inv_fy, inv_step;  // host-side reciprocals
     double step, max_half_len, min_depth, n_sigma, min_cov, max_cov;
     double q[4], t[3];    // T_C_R (unit quaternion x,y,z,w + translation)
     double qi[4], ti[3];  // T_R_C = T_C_R^-1 (ref:491), computed on the host
     double ti_norm;       // |t_RC| (ref:525)
-    double inv_ti_norm;   // 1 / |t_RC| (host-side division)
     double bd, wd, hd;    // border, width, height as doubles (inside() ref:222-224 without per-sample I2F)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
     const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (moments_kernel)
@@ -157,23 +157,9 @@ struct KParams {
 };
 
 // ----------------------------------------------------------------------------------------
-// small FP64 helpers
-struct D3 { double x, y, z; };
-__device__ __forceinline__ double dot3(const D3 &a, const D3 &b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
-__device__ __forceinline__ D3 cross3(const D3 &a, const D3 &b) {
-    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-}
-// Eigen Quaternion::_transformVector as used by Sophus SE3 * point
-__device__ __forceinline__ D3 qrot(const double q[4], const D3 &v) {
-    D3 qv{q[0], q[1], q[2]};
-    D3 uv = cross3(qv, v);
-    uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
-    D3 c = cross3(qv, uv);
-    return {v.x + q[3] * uv.x + c.x, v.y + q[3] * uv.y + c.y, v.z + q[3] * uv.z + c.z};
-}
-// normalize(px2cam(u,v)) ref:207-212,403: one reciprocal square root instead of sqrt + 3 divisions
-// (differs from the reference's divide-by-norm in the last ulp only)
-__device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v);
+// FP64 geometry: dmf_geometry.h (the reference's operation order, no FMA contraction, IEEE div / sqrt)
+typedef dmf_geom::V3 D3;
+__device__ __forceinline__ dmf_geom::Camera camera_of(const KParams &P) { return {P.fx, P.fy, P.cx, P.cy}; }
 // exact int -> double for |k| < 2^31 without the slow I2F.F64 path
 __device__ __forceinline__ double int2double_fast(int k) {
     return __hiloint2double(0x43300000, (int)((unsigned)k ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
@@ -182,10 +168,6 @@ __device__ __forceinline__ int row_of(const KParams &P, int rl) {
     const int b = rl / P.blk;
     const int pos = (b & 1) ? (P.cyc - 1 - P.ph) : P.ph;
     return P.row0 + (b * P.cyc + pos) * P.blk + (rl - b * P.blk);
-}
-// sample position parameter of iteration k of the loop ref:432, l_k = -half + step*k
-__device__ __forceinline__ double sample_l(double half, double step, int k) {
-    return fma(step, int2double_fast(k), -half);
 }
 // arg-max key: ncc in [-1,1] -> ncc + 3.0 in [2,4): the 52 mantissa bits are an order-preserving
 // fixed-point code with 2^-51 resolution.
@@ -238,42 +220,6 @@ __global__ void __launch_bounds__(256) ref_expand_kernel(const uint8_t *__restri
     refx[(size_t)y * width + x] = make_uint2(lo, hi);
 }
 
-__device__ __forceinline__ D3 unit_ray(const KParams &P, double u, double v) {
-    const double X = (u - P.cx) * P.inv_fx, Y = (v - P.cy) * P.inv_fy;
-    const double r = rsqrt(fma(X, X, fma(Y, Y, 1.0)));
-    return {X * r, Y * r, r};
-}
-
-// Epipolar search geometry of pixel (x,y) with state (mu, c2): ref:402-422.
-// f_ref: unit ray of the pixel, ref:402-403 (the caller may already hold it)
-__device__ __forceinline__ void search_geometry(const KParams &P, const D3 &f_ref, double mu, double c2, double &pmx, double &pmy,
-                                             double &lx, double &ly, double &half) {
-    const double sigma = sqrt(c2);  // ref:377
-    const D3 Rf = qrot(P.q, f_ref);  // T*(f*d) = d*(R f) + t
-    double d_min, d_max;
-    if (P.inverse_depth) {  // ref:407-410
-        const double inv_mu = 1.0 / mu;
-        d_min = 1.0 / (inv_mu + P.n_sigma * sigma);
-        d_max = 1.0 / (inv_mu - P.n_sigma * sigma);
-    } else {  // ref:412
-        d_min = mu - P.n_sigma * sigma;
-        d_max = mu + P.n_sigma * sigma;
-    }
-    if (d_min < P.min_depth) d_min = P.min_depth;  // ref:414
-    // cam2px ref:215-219 of the three points (one reciprocal per point)
-    const double rzm = 1.0 / fma(Rf.z, mu, P.t[2]), rz0 = 1.0 / fma(Rf.z, d_min, P.t[2]), rz1 = 1.0 / fma(Rf.z, d_max, P.t[2]);
-    pmx = fma(fma(Rf.x, mu, P.t[0]) * P.fx, rzm, P.cx);
-    pmy = fma(fma(Rf.y, mu, P.t[1]) * P.fy, rzm, P.cy);
-    const double p0x = fma(fma(Rf.x, d_min, P.t[0]) * P.fx, rz0, P.cx), p0y = fma(fma(Rf.y, d_min, P.t[1]) * P.fy, rz0, P.cy);
-    const double p1x = fma(fma(Rf.x, d_max, P.t[0]) * P.fx, rz1, P.cx), p1y = fma(fma(Rf.y, d_max, P.t[1]) * P.fy, rz1, P.cy);
-    lx = p1x - p0x; ly = p1y - p0y;  // ref:418
-    const double len2 = fma(lx, lx, ly * ly);
-    const double len = sqrt(len2);
-    half = 0.5 * len;  // ref:421
-    if (len2 > 0) { const double rl = 1.0 / len; lx *= rl; ly *= rl; }  // ref:420 (guarded normalize)
-    if (half > P.max_half_len) half = P.max_half_len;                    // ref:422
-}
-
 // ----------------------------------------------------------------------------------------
 // Per-pixel setup of one update, shared by setup_kernel (thread = pixel, state read from the maps) and advance_kernel
 // (thread = slot of the previous update, state straight from its fusion).
@@ -290,15 +236,12 @@ __device__ __forceinline__ void prepare_pixel(const KParams &P, PixelWork &w, bo
     w.n = 0; w.pmx = w.pmy = w.lx = w.ly = w.half = 0; w.st = make_int2(0, 0);
     w.active = have && !(w.c2 < P.min_cov || w.c2 > P.max_cov);  // ref:366 — NaN passes the gate
     if (w.active) {
-        if (!w.have_ray) w.f_ref = unit_ray(P, (double)w.x, (double)w.y);
-        search_geometry(P, w.f_ref, w.mu, w.c2, w.pmx, w.pmy, w.lx, w.ly, w.half);
-        // trip count of `for (l = -half; l <= half; l += step)` ref:432 (NaN half -> 0)
-        if (w.half >= 0) {
-            int n = (int)(2.0 * w.half * P.inv_step) + 1;
-            while (n > 0 && sample_l(w.half, P.step, n - 1) > w.half) --n;
-            while (n < 100000 && sample_l(w.half, P.step, n) <= w.half) ++n;
-            w.n = n;
-        }
+        const dmf_geom::Camera cam = camera_of(P);
+        if (!w.have_ray) w.f_ref = dmf_geom::unit_ray(cam, (double)w.x, (double)w.y);  // ref:402-403
+        const dmf_geom::Segment sg = dmf_geom::search_segment(cam, P.q, P.t, w.f_ref, w.mu, sqrt(w.c2) /* ref:377 */, P.n_sigma,
+                                                              P.min_depth, P.max_half_len, P.inverse_depth != 0);
+        w.pmx = sg.pm.x; w.pmy = sg.pm.y; w.lx = sg.dir.x; w.ly = sg.dir.y; w.half = sg.half;
+        w.n = dmf_geom::trip_count(w.half, P.step);  // `for (l = -half; l <= half; l += step)` ref:432, accumulated l
         w.st = __ldg(&P.refstat[(size_t)w.y * P.stat_pitch + w.x]);
     }
 }
@@ -664,24 +607,18 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             int best_k = -1;
             int hix = -1, hiy = -1;  // integer position whose SampleInts are held
             SampleInts si{};
-            // position of the first sample; inside the loop the position of sample j+1 is computed
-            // before the NCC of sample j so its FP64 chain is off the critical path
+            // l of the unit's first sample: k0 additions of the step, as the reference accumulates them (ref:432);
+            // inside the loop the position of sample j+1 is computed before the NCC of sample j (off the critical path)
             double sx, sy;
-            double kd = int2double_fast(k0);  // sample index as a double: l_k = fma(step, k, -half) as in sample_l()
-            {
-                const double l = fma(P.step, kd, -half);
-                sx = fma(l, dir.x, pm.x);  // ref:433
-                sy = fma(l, dir.y, pm.y);
-            }
+            double l = dmf_geom::sample_l_acc(half, P.step, k0);
+            sx = __dadd_rn(pm.x, __dmul_rn(l, dir.x));  // ref:433, unfused like the reference build
+            sy = __dadd_rn(pm.y, __dmul_rn(l, dir.y));
 #pragma unroll 1
             for (int j = 0; j < L; ++j) {
                 const double cx = sx, cy = sy;
-                {
-                    kd += 1.0;
-                    const double l = fma(P.step, kd, -half);
-                    sx = fma(l, dir.x, pm.x);
-                    sy = fma(l, dir.y, pm.y);
-                }
+                l = __dadd_rn(l, P.step);
+                sx = __dadd_rn(pm.x, __dmul_rn(l, dir.x));
+                sy = __dadd_rn(pm.y, __dmul_rn(l, dir.y));
                 // inside() ref:222-224
                 const bool ok = cx >= P.bd && cy >= P.bd && cx + P.bd < P.wd && cy + P.bd <= P.hd;
                 if (!ok) continue;
@@ -724,45 +661,15 @@ __device__ __forceinline__ bool fuse_slot(const KParams &P, unsigned slot, int &
     const bool accepted = key_has_winner(key) && !(key_ncc(key) < P.ncc_thresh);  // ref:443; sentinel: nothing beat -1.0
     if (accepted) {
         const int k = key_index(key);
-        const double ex = dir.x, ey = dir.y;
-        const double l = sample_l(half, P.step, k);
-        const double cxp = fma(l, ex, pm.x), cyp = fma(l, ey, pm.y);  // pt_curr
-        // updateDepthFilter ref:482-567
-        const D3 f_ref = unit_ray(P, (double)x, (double)y);
+        const dmf_geom::Camera cam = camera_of(P);
+        const dmf_geom::V2 pmv{pm.x, pm.y}, dv{dir.x, dir.y};
+        const dmf_geom::V2 pt_curr = dmf_geom::sample_pos(pmv, dv, dmf_geom::sample_l_acc(half, P.step, k));  // best_px_curr ref:440
+        const D3 f_ref = dmf_geom::unit_ray(cam, (double)x, (double)y);
         f_ref_out = f_ref; have_ray = true;
-        const D3 f_curr = unit_ray(P, cxp, cyp);
-        const D3 t{P.ti[0], P.ti[1], P.ti[2]};
-        const D3 f2 = qrot(P.qi, f_curr);
-        const double b0 = dot3(t, f_ref), b1 = dot3(t, f2);
-        const double a00 = dot3(f_ref, f_ref), a01 = -dot3(f_ref, f2), a11 = -dot3(f2, f2);
-        const double a10 = -a01;
-        // 2x2 solve (the reference uses ColPivHouseholderQR; Cramer differs by O(cond*eps))
-        const double rdet = 1.0 / (a00 * a11 - a01 * a10);
-        const double ans0 = (b0 * a11 - a01 * b1) * rdet;
-        const double ans1 = (a00 * b1 - a10 * b0) * rdet;
-        const D3 pe{0.5 * (ans0 * f_ref.x + (t.x + ans1 * f2.x)), 0.5 * (ans0 * f_ref.y + (t.y + ans1 * f2.y)),
-                    0.5 * (ans0 * f_ref.z + (t.z + ans1 * f2.z))};
-        const double depth_est = sqrt(dot3(pe, pe));
-        // uncertainty of one pixel along the epipolar line ref:525-533.  The reference takes
-        // alpha = acos(ca), beta' = acos(cb), gamma = pi - alpha - beta' and p' = |t| sin(beta')/sin(gamma);
-        // with sin(acos(c)) = sqrt(1 - c^2) on [0,pi] and sin(gamma) = sin(alpha + beta') this needs no
-        // transcendental call (|c| > 1 by rounding gives NaN on both routes).
-        const double t_norm = P.ti_norm;
-        const double rt = P.inv_ti_norm;
-        const double ca = dot3(f_ref, t) * rt;
-        const D3 fcp = unit_ray(P, cxp + ex, cyp + ey);
-        const double cb = -dot3(fcp, t) * rt;
-        const double sa = sqrt(fma(-ca, ca, 1.0)), sb = sqrt(fma(-cb, cb, 1.0));
-        const double p_prime = t_norm * sb / fma(sa, cb, ca * sb);
-        const double d_cov = P.inverse_depth ? (1.0 / p_prime - 1.0 / depth_est) : (p_prime - depth_est);
-        const double d_cov2 = d_cov * d_cov;
-        const double mu0 = P.inverse_depth ? 1.0 / mu : mu;
-        const double meas = P.inverse_depth ? (c2 * 1.0 / depth_est) : (c2 * depth_est);
-        const double rden = 1.0 / (c2 + d_cov2 + 1e-10);
-        const double mu_fuse = (d_cov2 * mu0 + meas) * rden;
-        const double sig_fuse = (c2 * d_cov2) * rden;
-        mu = P.inverse_depth ? 1.0 / mu_fuse : mu_fuse;  // ref:560-562
-        c2 = sig_fuse;                                   // ref:564
+        // updateDepthFilter ref:482-567 in the reference's operation order (ColPivHouseholderQR restated)
+        const dmf_geom::Fused fu = dmf_geom::fuse(cam, P.qi, P.ti, P.ti_norm, f_ref, pt_curr, dv, mu, c2, P.inverse_depth != 0);
+        mu = fu.mu;       // ref:560-562
+        c2 = fu.sigma2;   // ref:564
         P.depth[(size_t)y * P.state_pitch + x] = mu;
         P.cov2[(size_t)y * P.state_pitch + x] = c2;
     }
@@ -902,9 +809,9 @@ __device__ __forceinline__ bool cloud_valid(double dist, double var, double max_
 }
 
 __global__ void __launch_bounds__(256) cloud_count_kernel(const double *__restrict__ dist, const double *__restrict__ var, int pitch,
-                                                          int x0, int x1, int y0, double max_variance,
+                                                          int x0, int x1, const int *__restrict__ rows, double max_variance,
                                                           unsigned int *__restrict__ row_count) {
-    const int y = y0 + blockIdx.x;
+    const int y = rows[blockIdx.x];  // owned image rows in ascending order (a band, or the blocks of a cyclic context)
     unsigned n = 0;
     for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x)
         n += cloud_valid(dist[(size_t)y * pitch + x], var[(size_t)y * pitch + x], max_variance) ? 1u : 0u;
@@ -947,11 +854,11 @@ __global__ void __launch_bounds__(1024) cloud_scan_kernel(unsigned int *row_coun
 
 __global__ void __launch_bounds__(256) cloud_write_kernel(const double *__restrict__ dist, const double *__restrict__ var, int pitch,
                                                           const uint8_t *__restrict__ color, int color_pitch, int channels,
-                                                          int x0, int x1, int y0, double max_variance, double cx, double cy,
+                                                          int x0, int x1, const int *__restrict__ rows, double max_variance, double cx, double cy,
                                                           double fx, double fy, const unsigned int *__restrict__ row_offset,
                                                           float *__restrict__ xyz, uint8_t *__restrict__ rgb,
                                                           unsigned long long capacity) {
-    const int y = y0 + blockIdx.x;
+    const int y = rows[blockIdx.x];
     __shared__ unsigned s_warp[8];
     __shared__ unsigned s_run;
     if (threadIdx.x == 0) s_run = row_offset[blockIdx.x];
@@ -974,10 +881,11 @@ __global__ void __launch_bounds__(256) cloud_write_kernel(const double *__restri
             const unsigned long long slot = (unsigned long long)s_run + before + __popc(bal & ((1u << lane) - 1u));
             if (slot < capacity) {
                 // point = normalize((u-cx)/fx, (v-cy)/fy, 1) * distance   (:68-73), stored as float like PointXYZRGB
+                // (no FMA contraction: the floats are bit-identical to the reference's g++ build)
                 double px = ((double)x - cx) / fx, py = ((double)y - cy) / fy, pz = 1.0;
-                const double z = px * px + (py * py + pz * pz);
+                const double z = __dadd_rn(__dmul_rn(px, px), __dadd_rn(__dmul_rn(py, py), __dmul_rn(pz, pz)));
                 if (z > 0) { const double nrm = sqrt(z); px /= nrm; py /= nrm; pz /= nrm; }
-                xyz[3 * slot + 0] = (float)(px * d); xyz[3 * slot + 1] = (float)(py * d); xyz[3 * slot + 2] = (float)(pz * d);
+                xyz[3 * slot + 0] = (float)__dmul_rn(px, d); xyz[3 * slot + 1] = (float)__dmul_rn(py, d); xyz[3 * slot + 2] = (float)__dmul_rn(pz, d);
                 const uint8_t *c = color + (size_t)y * color_pitch + (size_t)x * channels;
                 rgb[3 * slot + 0] = channels >= 3 ? c[2] : c[0];  // r (:79-81: b,g,r = data[0..2])
                 rgb[3 * slot + 1] = channels >= 3 ? c[1] : c[0];

@@ -26,8 +26,9 @@ POSE_FILE = "first_200_frames_traj_over_table_input_sequence.txt"
 DEPTH_FILE = "depthmaps/scene_000.depth"
 
 
-def read_dataset(path: str, width: int = 640, height: int = 480) -> Tuple[List[str], List[SE3], np.ndarray]:
-    """Returns (image file paths, poses T_WC, reference depth map in metres (H, W) float64)."""
+def read_poses(path: str) -> Tuple[List[str], List[SE3]]:
+    """The pose list (ref:322-337): (image file paths, poses T_WC).  Complete entries only: the reference's
+    `while (!fin.eof())` loop appends one bogus entry after a trailing newline, which its driver skips (ref:288)."""
     root = Path(path)
     files: List[str] = []
     poses: List[SE3] = []
@@ -37,8 +38,15 @@ def read_dataset(path: str, width: int = 640, height: int = 480) -> Tuple[List[s
     for i in range(0, len(tokens) - 7, 8):
         name = tokens[i]
         tx, ty, tz, qx, qy, qz, qw = (float(v) for v in tokens[i + 1:i + 8])
-        files.append(str(root / "images" / name))
+        files.append(str(root) + "/images/" + name)  # path + "/images/" + image, ref:332
         poses.append(SE3.from_quat_trans(qx, qy, qz, qw, tx, ty, tz))
+    return files, poses
+
+
+def read_dataset(path: str, width: int = 640, height: int = 480) -> Tuple[List[str], List[SE3], np.ndarray]:
+    """Returns (image file paths, poses T_WC, reference depth map in metres (H, W) float64)."""
+    root = Path(path)
+    files, poses = read_poses(path)
     depth = np.loadtxt(root / DEPTH_FILE, dtype=np.float64).reshape(-1)
     if depth.size != width * height:
         raise ValueError(f"{DEPTH_FILE}: expected {width * height} values, found {depth.size}")

@@ -18,8 +18,10 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 import oracle  # noqa: E402
 from slamplay_b200.synth import make_sequence  # noqa: E402
+from parity import synthetic_state  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 N_FRAMES = 6
@@ -82,7 +84,46 @@ def main():
         fu[i] = list(out)
     np.savez_compressed(HERE / "remode640_ref_units.npz", frame_ref=0, frame_cur=3, pose=np.array(list(T.q) + list(T.t)),
                         rx=rx, ry=ry, cx=cx, cy=cy, ncc=ncc, mu=mu, sigma=sigma, search=es, dirs=dirs, dval=dval, cval=cval, fuse=fu)
+    make_next_rows(seq, frames)
     print("wrote", [p.name for p in HERE.glob("*.npz")])
+
+
+def make_next_rows(seq, frames):
+    """Fixtures of the 'next' rows from the compiled reference: evaludateDepth ref:569-590,
+    getMaskFromVariance ref:199-204, getPointCloudFromImageAndDistance (the reference's own header), the inverse-depth
+    variant (ref:63, libdmf_ref_inv.so), readDatasetFiles ref:317-352 and the pose chain ref:289-290."""
+    import tempfile
+
+    from slamplay_b200.remode import POSE_FILE, write_dataset
+    h, w = seq.shape
+    depth, cov2, truth = synthetic_state(h, w)
+    thr = 2e-4  # good_cov ref:89
+    rms = oracle.ref_evaluate_depth(truth, depth, cov2, thr)
+    mask = oracle.ref_variance_mask(cov2, thr)
+    color = np.ascontiguousarray(np.stack([frames[0], 255 - frames[0], frames[0] // 2], axis=-1))
+    xyz, rgb = oracle.ref_point_cloud(color, depth, mask)
+    # inverse-depth variant: 4 updates from (3.0, 0.5)
+    seqi = make_sequence("remode_640x480", n_frames=N_FRAMES, inverse_depth=True)
+    di, ci = np.full((h, w), 3.0), np.full((h, w), 0.5)
+    inv_sha = []
+    for i in range(1, 5):
+        T = seqi.T_C_R(i)
+        oracle.ref_update(frames[0], frames[i], T.q, T.t, di, ci, inverse=True)
+        inv_sha.append([sha(di), sha(ci)])
+    # reader: a 3-frame REMODE-layout directory written by our writer, read by the reference's readDatasetFiles
+    with tempfile.TemporaryDirectory() as tmp:
+        _, gt = seq.render_host(0, with_distance=True)
+        write_dataset(tmp, seq, frames[:3], gt)
+        files, poses, ref_depth = oracle.ref_read_dataset(tmp)
+        pose_txt = open(Path(tmp) / POSE_FILE).read()
+    T_C_R = np.array([oracle.ref_compose_T_C_R(poses[0], poses[k]) for k in range(3)])
+    np.savez_compressed(
+        HERE / "remode640_ref_next.npz", max_variance=thr, rms=rms, mask_sha=sha(mask), mask_rows=mask[::32].copy(),
+        cloud_n=len(xyz), cloud_xyz_sha=sha(xyz), cloud_rgb_sha=sha(rgb), cloud_xyz_head=xyz[:64].copy(), cloud_rgb_head=rgb[:64].copy(),
+        cloud_xyz_stride=xyz[::997].copy(),
+        inv_per_frame_sha=np.array(inv_sha), inv_depth_rows=di[::16].copy(), inv_cov2_rows=ci[::16].copy(), inv_row_step=16,
+        reader_pose_txt=pose_txt, reader_poses=poses[:3].copy(), reader_n_entries=len(files), reader_T_C_R=T_C_R,
+        reader_depth_sha=sha(ref_depth), state_sha=np.array([sha(depth), sha(cov2), sha(truth)]))
 
 
 if __name__ == "__main__":

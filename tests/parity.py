@@ -32,3 +32,19 @@ def class_mismatch(p, c_test, c_ref, rows=None):
 def flag_mismatch(p, f_test, f_ref, rows=None):
     ys, xs = interior(p, rows)
     return float((f_test[ys][:, xs] != f_ref[ys][:, xs]).mean())
+
+
+def synthetic_state(h=480, w=640):
+    """Deterministic state / truth maps from integer hashes (no RNG stream to drift): depth in [1.5, 3.5), cov2 log-uniform
+    over [1e-5, 10) with a few NaN and zero-depth pixels, truth = depth + a small offset."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.uint64)
+    hsh = lambda a, b: ((x * np.uint64(a)) ^ (y * np.uint64(b))) % np.uint64(1000003)
+    u1 = hsh(73856093, 19349663).astype(np.float64) / 1000003.0
+    u2 = hsh(83492791, 49979687).astype(np.float64) / 1000003.0
+    u3 = hsh(2654435761, 40503).astype(np.float64) / 1000003.0
+    depth = 1.5 + 2.0 * u1
+    cov2 = 10.0 ** (-5.0 + 6.0 * u2)
+    truth = depth + 0.05 * (u3 - 0.5)
+    depth[::53, ::47] = 0.0      # "not measured" (pointcloud_from_image_depth.h:66)
+    cov2[::41, ::59] = np.nan    # NaN variance: counted by evaludateDepth? (NaN >= t is false -> counted), mask 255
+    return depth, cov2, truth

@@ -493,3 +493,70 @@ def test_accessors_see_the_deferred_fusion(DF, seq640):
     d2, c2 = g.download_state()
     g.close()
     assert np.array_equal(d1, d2, equal_nan=True) and np.array_equal(c1, c2, equal_nan=True)
+
+
+# ---- "next" rows against fixtures generated from the compiled reference ------------------------------
+def test_next_rows_against_reference_fixtures(DF, seq640):
+    """evaludateDepth ref:569-590, getMaskFromVariance ref:199-204 and getPointCloudFromImageAndDistance
+    (utils/pointcloud/pointcloud_from_image_depth.h:42-89) on the device vs tests/golden/remode640_ref_next.npz, which
+    tests/golden/make_golden.py produced by calling the reference's own functions; also through a block-cyclic split."""
+    from parity import synthetic_state
+    nxt = np.load(G / "remode640_ref_next.npz")
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    depth, cov2, truth = synthetic_state(h, w)
+    thr = float(nxt["max_variance"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    f = DF(p)
+    f.upload_state(depth, cov2)
+    f.set_truth(truth)
+    s, n = f.evaluate_depth(thr)
+    mask = f.variance_mask(thr)
+    color = np.ascontiguousarray(np.stack([frames[0], 255 - frames[0], frames[0] // 2], axis=-1))
+    xyz, rgb = f.point_cloud(color, thr)
+    f.close()
+    assert np.isclose((s / n) ** 0.5, float(nxt["rms"]), rtol=1e-10)
+    assert sha(mask) == str(nxt["mask_sha"])
+    assert len(xyz) == int(nxt["cloud_n"])
+    assert sha(rgb) == str(nxt["cloud_rgb_sha"])
+    assert np.array_equal(xyz[:64], nxt["cloud_xyz_head"]) and np.array_equal(xyz[::997], nxt["cloud_xyz_stride"])
+    assert sha(xyz) == str(nxt["cloud_xyz_sha"])
+    # block-cyclic contexts: each returns the points of its own rows, in scan order
+    b = p.border
+    valid = (depth != 0) & (mask == 255)
+    per_row = np.zeros(h + 1, np.int64)
+    per_row[b + 1:h - b + 1] = valid[b:h - b, b:w - b].sum(axis=1)
+    off = np.cumsum(per_row)
+    total = 0
+    for part in range(2):
+        g = DF(p, cyclic=(8, 2, part))
+        g.upload_state(depth, cov2)
+        x2, r2 = g.point_cloud(color, thr)
+        rows = g.owned_rows()
+        g.close()
+        idx = np.concatenate([np.arange(off[y], off[y + 1]) for y in rows])
+        assert np.array_equal(x2, xyz[idx]) and np.array_equal(r2, rgb[idx])
+        total += len(x2)
+    assert total == len(xyz)
+
+
+def test_inverse_depth_variant_against_reference_fixture(DF):
+    """USE_INVERSE_DEPTH_FOR_FILTERING 1 (ref:63): 4 updates from (3.0, 0.5) vs the variant translation unit's maps."""
+    nxt = np.load(G / "remode640_ref_next.npz")
+    seq = make_sequence("remode_640x480", n_frames=6, inverse_depth=True)
+    p = seq.params
+    frames = [seq.render_host(i) for i in range(5)]
+    f = DF(p)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 0.5)
+    for i in range(1, 5):
+        f.update(frames[i], seq.T_C_R(i))
+    d, c = f.download_state()
+    f.close()
+    st = int(nxt["inv_row_step"])
+    rows = range(0, 480, st)
+    d_ref, c_ref = _expand(nxt["inv_depth_rows"], st, d.shape), _expand(nxt["inv_cov2_rows"], st, c.shape)
+    assert depth_agreement(p, d, d_ref, rows) >= MIN_DEPTH_AGREE
+    assert depth_agreement(p, d, d_ref, rows, rtol=1e-6) > 0.999
+    assert class_mismatch(p, c, c_ref, rows) <= MAX_DECISION_MISMATCH

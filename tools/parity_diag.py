@@ -72,6 +72,10 @@ def main():
     first_class = np.zeros(n_s, np.int8)          # 1 gate 2 trip 3 argmax 4 accept
     first_info = {}                               # (row index, col) -> details
     pre_rel = np.zeros(n_s)                       # state difference just before the first divergence
+    drift_frame = np.full(n_s, -1, np.int32)      # first update after which the states differ by more than 1e-9 (relative)
+    drift_epi = np.full(n_s, np.nan)              # distance (px) of the pixel from the epipole of that update's frame
+    xx = np.arange(b, w - b, dtype=np.float64)[None, :]
+    yy = ys.astype(np.float64)[:, None]
     worst_flag = 0.0
     per_frame = []
     dg_prev = np.full(n_s, 3.0)
@@ -131,6 +135,19 @@ def main():
         do_prev, co_prev = d_o[ys][:, xs].copy(), c_o[ys][:, xs].copy()
         both_nan = np.isnan(dg_prev) & np.isnan(do_prev)
         ok3 = (np.abs(dg_prev - do_prev) <= 1e-3 * np.abs(do_prev)) | both_nan
+        # numeric drift of the state while every decision so far was equal: where is the pixel relative to the epipole?
+        def _rel(a, r):
+            v = np.abs(a - r) / np.maximum(np.abs(r), 1e-300)
+            return np.where(np.isnan(a) & np.isnan(r), 0.0, np.where(np.isnan(v), np.inf, v))
+        rel_now = np.maximum(_rel(dg_prev, do_prev), _rel(cg_prev, co_prev))
+        newd = (rel_now > 1e-9) & (drift_frame < 0) & ((first_frame < 0) | (first_frame == i))
+        if newd.any():
+            Ti = T.inverse()
+            ex = p.fx * Ti.t[0] / Ti.t[2] + p.cx if Ti.t[2] != 0 else np.inf
+            ey = p.fy * Ti.t[1] / Ti.t[2] + p.cy if Ti.t[2] != 0 else np.inf
+            dist = np.sqrt((xx - ex) ** 2 + (yy - ey) ** 2)
+            drift_frame[newd] = i
+            drift_epi[newd] = dist[newd]
         per_frame.append({"update": i, "flag_mismatch": mism, "active_frac": float(act.mean()), "new_divergences": int(new.sum()),
                           "depth_within_1e-3": float(ok3.mean())})
         if i <= 3 or i % 25 == 0 or i == F - 1:
@@ -158,6 +175,19 @@ def main():
         "pre_divergence_state_rel_diff": {"median": float(np.median(pre_rel[first_frame >= 0])) if (first_frame >= 0).any() else None,
                                           "max": float(pre_rel[first_frame >= 0].max()) if (first_frame >= 0).any() else None},
         "first_divergence_update_histogram": {str(k): int(v) for k, v in zip(*np.unique(first_frame[first_frame >= 0] // 25 * 25, return_counts=True))},
+    }
+    drifted = drift_frame >= 0
+    decided_first = (first_frame >= 0) & (~drifted | (first_frame <= drift_frame))
+    out["root_cause"] = {
+        "pixels_whose_state_drifted_>1e-9_before_or_without_any_decision_difference": int((drifted & ~decided_first).sum()),
+        "pixels_whose_first_difference_was_a_decision_with_states_equal_to_1e-9": int(decided_first.sum()),
+        "deviating(>1e-3)_by_root": {"state_drift_first": int((bad & drifted & ~decided_first).sum()), "decision_first": int((bad & decided_first).sum()),
+                                     "neither": int((bad & ~drifted & (first_frame < 0)).sum())},
+        "epipole_distance_px_at_first_drift": ({"median": float(np.nanmedian(drift_epi[drifted & ~decided_first])),
+                                                "p90": float(np.nanquantile(drift_epi[drifted & ~decided_first], 0.9)),
+                                                "max": float(np.nanmax(drift_epi[drifted & ~decided_first]))}
+                                               if (drifted & ~decided_first).any() else None),
+        "max_state_rel_diff_among_pixels_without_any_difference_flag": float(np.nanmax(np.where(~drifted & (first_frame < 0), rel_d, 0.0))),
     }
     # near-tie evidence for the argmax class: |ncc_gpu - ncc_ref| of the two different winners
     am = [v for v in first_info.values() if v["class"] == 3]
