@@ -318,6 +318,20 @@ void colpiv_qr_solve2(const double a_in[2][2], const double b_in[2], double x_ou
 
 struct FuseOut { double depth_est, d_cov2, mu_fuse, sigma_fuse2; };
 
+// Diagnostic only (dmo_set_libm_perturbation, default 0 = off): moves the two acos results of ref:527,531 by up to
+// +-n ulp, pseudo-randomly per call, to measure how far a libm that is not bit-identical to glibc (CUDA's acos / sin
+// are specified to 1-2 ulp) can move the filter state.  Never enabled by tests that pin the oracle.
+int g_perturb_ulp = 0;
+inline double nudge(double v, double key) {
+    uint64_t h;
+    std::memcpy(&h, &key, 8);
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+    int k = int(h % uint64_t(2 * g_perturb_ulp + 1)) - g_perturb_ulp;
+    for (; k > 0; --k) v = std::nextafter(v, 1e300);
+    for (; k < 0; ++k) v = std::nextafter(v, -1e300);
+    return v;
+}
+
 // ref:482-567
 FuseOut update_depth_filter(const Cam &c, const V2 &pt_ref, const V2 &pt_curr, const SE3 &T_C_R,
                             const V2 &dir, double depth_val, double cov2_val) {
@@ -342,11 +356,15 @@ FuseOut update_depth_filter(const Cam &c, const V2 &pt_ref, const V2 &pt_curr, c
     const double depth_estimation = norm(p_esti);
 
     const double t_norm = norm(t);
-    const double alpha = std::acos(dot(f_ref, t) / t_norm);
+    double alpha = std::acos(dot(f_ref, t) / t_norm);
     V3 f_curr_prime = px2cam(c, V2{pt_curr.x + dir.x, pt_curr.y + dir.y});
     normalize(f_curr_prime);
     const V3 mt{-t.x, -t.y, -t.z};
-    const double beta_prime = std::acos(dot(f_curr_prime, mt) / t_norm);  // not rotated into the ref frame (ref:529-531)
+    double beta_prime = std::acos(dot(f_curr_prime, mt) / t_norm);  // not rotated into the ref frame (ref:529-531)
+    if (g_perturb_ulp) {  // diagnostic (tools/libm_sensitivity.py): what a libm that differs by a few ulp does to the filter
+        alpha = nudge(alpha, pt_ref.x * 31.0 + pt_ref.y * 17.0 + pt_curr.x);
+        beta_prime = nudge(beta_prime, pt_ref.x * 13.0 + pt_ref.y * 29.0 + pt_curr.y);
+    }
     const double gamma = M_PI - alpha - beta_prime;
     const double p_prime_norm = t_norm * std::sin(beta_prime) / std::sin(gamma);
     const double d_cov = c.inverse_depth ? (1.0 / p_prime_norm - 1.0 / depth_estimation)
@@ -603,6 +621,7 @@ long long dmo_point_cloud(const dmf_params *p, const uint8_t *color, size_t colo
 }
 
 int dmo_max_threads(void);
+void dmo_set_libm_perturbation(int ulp) { g_perturb_ulp = ulp < 0 ? 0 : ulp; }
 
 }  // extern "C"
 
