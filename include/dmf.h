@@ -139,8 +139,10 @@ int dmf_download_state(dmf_ctx *ctx, double *depth, size_t depth_step,
  * One update() call (:355-393) against the current frame `curr` (CV_8UC1) with
  * T_C_R given as Sophus stores it: unit quaternion (x,y,z,w) + translation.
  * Asynchronous on the context stream; the host frame is consumed (copied to a
- * device staging buffer) before return unless it is pinned memory obtained from
- * dmf_alloc_pinned(), in which case it must stay untouched until dmf_sync().
+ * device staging buffer) before return unless it is page-locked memory known to CUDA
+ * (dmf_alloc_pinned(), cudaMallocHost, cudaHostRegister — detected with
+ * cudaPointerGetAttributes), in which case it is copied straight from the caller's
+ * buffer and must stay untouched until dmf_sync().
  * _device: frame already in HBM on ctx's device (e.g. received by NCCL broadcast);
  * the kernels that read it are ordered after everything previously enqueued on
  * `wait_stream` (a cudaStream_t).  With wait_stream == NULL the frame must be
@@ -153,6 +155,17 @@ int dmf_update(dmf_ctx *ctx, const uint8_t *curr_host, size_t step,
                const double q_xyzw[4], const double t_xyz[3]);
 int dmf_update_device(dmf_ctx *ctx, const uint8_t *curr_dev, size_t step,
                       const double q_xyzw[4], const double t_xyz[3], void *wait_stream);
+
+/*
+ * STRICT drop-in form of update() (:355-393, call site :291) in one call: `depth` / `depth_cov2` (host, CV_64F) are
+ * read, updated against `curr` and valid again on return, as the reference's caller reads them after every call
+ * (:292-300).  The reference image is uploaded (and its patch statistics recomputed) only when its CONTENT changes
+ * (64-bit hash); the maps are uploaded only when they differ from what the previous call returned (compared against a
+ * pinned shadow copy); downloads go through pinned memory.  The context must own every interior row.
+ */
+int dmf_update_strict(dmf_ctx *ctx, const uint8_t *ref_host, size_t ref_step, const uint8_t *curr_host, size_t curr_step,
+                      const double q_xyzw[4], const double t_xyz[3], double *depth, size_t depth_step,
+                      double *depth_cov2, size_t cov2_step);
 
 /*
  * The Gaussian fusion (:546-564) of an update is deferred: it runs inside the next

@@ -5,7 +5,7 @@
  * download and absent here, so sequences of the same shape are rendered instead.
  *
  * dmf_synth_render_host   lives in slamplay_b200/libdmf_synth_cpu.so (g++, OpenMP)
- * dmf_synth_render_device lives in slamplay_b200/libdmf.so            (CUDA, sm_100a)
+ * dmf_synth_render_device lives in slamplay_b200/libdmf_synth.so      (CUDA, sm_100a; NOT in the product library libdmf.so)
  * Both evaluate slamplay_b200/csrc/synth_scene.h with FMA contraction off and produce
  * bit-identical images.
  */

@@ -4,7 +4,13 @@ A from-scratch sm_100a implementation of ONE hot path of luigifreda/slamplay: th
 `update()` loop of dense_mapping/test_monocular_mapping.cpp (epipolar NCC search + depth-filter
 fusion), behind the reference's own call surface.  See DESIGN.md.
 """
-from .se3 import SE3, relative_pose  # noqa: F401
+import os as _os
+
+# The frame ring (frame_ring.py) orders streams of different processes with stream memory operations: a stream that waits
+# on a flag must not share a hardware queue with the stream that will set it.  Effective when set before CUDA initialises.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .se3 import SE3, relative_pose  # noqa: E402,F401
 
 __all__ = ["SE3", "relative_pose", "DepthFilter", "update", "default_params", "DmfError"]
 

@@ -86,6 +86,7 @@ DMF_SYMBOLS = {
     "dmf_download_state": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
     "dmf_update": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double)]),
     "dmf_update_device": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double), _vp]),
+    "dmf_update_strict": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_double), _P(C.c_double), _vp, C.c_size_t, _vp, C.c_size_t]),
     "dmf_flush": (C.c_int, [_vp]),
     "dmf_sync": (C.c_int, [_vp]),
     "dmf_set_timing": (C.c_int, [_vp, C.c_int]),
@@ -138,9 +139,20 @@ def load_dmf() -> C.CDLL:
                 "(needs nvcc). The depth-filter path has no CPU fallback.")
         lib = C.CDLL(str(path))
         _bind(lib, DMF_SYMBOLS)
-        _bind(lib, SYNTH_DEVICE_SYMBOLS)
         _cache["dmf"] = lib
     return _cache["dmf"]
+
+
+def load_synth_cuda() -> C.CDLL:
+    """slamplay_b200/libdmf_synth.so: the CUDA renderer of the synthetic inputs (not part of the product library)."""
+    if "synth_cuda" not in _cache:
+        path = PKG / "libdmf_synth.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with `python -m slamplay_b200.build`")
+        lib = C.CDLL(str(path))
+        _bind(lib, SYNTH_DEVICE_SYMBOLS)
+        _cache["synth_cuda"] = lib
+    return _cache["synth_cuda"]
 
 
 def load_synth_cpu() -> C.CDLL:

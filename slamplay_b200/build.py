@@ -52,10 +52,10 @@ def _stale(target: Path, sources: list[Path]) -> bool:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
-    """libdmf.so = C ABI (include/dmf.h) + kernels + the device-side synthetic renderer."""
+    """libdmf.so = C ABI (include/dmf.h): kernels, frame ring, pipe micro-benchmarks — the product library."""
     target = PKG / "libdmf.so"
-    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "dmf_geometry.h", CSRC / "synth.cu", CSRC / "synth_scene.h", CSRC / "microbench.cu", CSRC / "frame_ring.cu", CSRC / "dmf_internal.h",
-            ROOT / "include" / "dmf.h", ROOT / "include" / "dmf_synth.h"]
+    srcs = [CSRC / "dmf_api.cu", CSRC / "dmf_kernels.cuh", CSRC / "dmf_geometry.h", CSRC / "microbench.cu", CSRC / "frame_ring.cu",
+            CSRC / "dmf_internal.h", ROOT / "include" / "dmf.h"]
     if not force and not _stale(target, srcs):
         return target
     nvcc = _nvcc()
@@ -64,15 +64,30 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     ccbin = ["-ccbin", _host_cxx()]
     extra = os.environ.get("DMF_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DDMF_NCC_MIN_BLOCKS=3
     out1 = _run([nvcc, *NVCC_FLAGS, *extra, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")], build / "dmf_api.ptxas.log")
-    # the renderer must not contract a*b+c into FMA (bit-identical with the g++ build)
-    out2 = _run([nvcc, *NVCC_FLAGS, *ccbin, "-fmad=false", "-c", str(CSRC / "synth.cu"), "-o", str(build / "synth.o")], build / "synth.ptxas.log")
     _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "microbench.cu"), "-o", str(build / "microbench.o")], build / "microbench.ptxas.log")
     _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "frame_ring.cu"), "-o", str(build / "frame_ring.o")], build / "frame_ring.ptxas.log")
-    _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "synth.o"), str(build / "microbench.o"),
+    _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "microbench.o"),
           str(build / "frame_ring.o"), "-lcudart", "-lrt"])
     if verbose:
         print(out1)
-        print(out2)
+    return target
+
+
+def build_synth_cuda(force: bool = False) -> Path:
+    """libdmf_synth.so = the CUDA renderer of the synthetic input sequences (include/dmf_synth.h).  An INPUT GENERATOR
+    for tests and benchmarks, kept out of the product library so that a process which only needs inputs (bench.py
+    --impl reference) never loads libdmf.so."""
+    target = PKG / "libdmf_synth.so"
+    srcs = [CSRC / "synth.cu", CSRC / "synth_scene.h", ROOT / "include" / "dmf_synth.h"]
+    if not force and not _stale(target, srcs):
+        return target
+    nvcc = _nvcc()
+    build = PKG / "build"
+    build.mkdir(exist_ok=True)
+    ccbin = ["-ccbin", _host_cxx()]
+    # the renderer must not contract a*b+c into FMA (bit-identical with the g++ build)
+    _run([nvcc, *NVCC_FLAGS, *ccbin, "-fmad=false", "-c", str(CSRC / "synth.cu"), "-o", str(build / "synth.o")], build / "synth.ptxas.log")
+    _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "synth.o"), "-lcudart"])
     return target
 
 
@@ -87,7 +102,7 @@ def build_synth_cpu(force: bool = False) -> Path:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> dict[str, Path]:
-    return {"libdmf": build_cuda(force, verbose), "libdmf_synth_cpu": build_synth_cpu(force)}
+    return {"libdmf": build_cuda(force, verbose), "libdmf_synth": build_synth_cuda(force), "libdmf_synth_cpu": build_synth_cpu(force)}
 
 
 if __name__ == "__main__":

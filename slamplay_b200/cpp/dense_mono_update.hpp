@@ -17,13 +17,17 @@
 //        whole sequence; only the u8 frame and the pose cross PCIe per update; download() on demand.
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
 #include <memory>
+#include <string>
 #include <tuple>
+#include <vector>
 
 #include "../../include/dmf.h"
 
@@ -41,6 +45,13 @@ inline void pose_of(const SE3d &T, double q[4], double t[3]) {
     const auto &tr = T.translation();
     t[0] = tr[0]; t[1] = tr[1]; t[2] = tr[2];
 }
+// SE3d(Quaterniond(qw,qx,qy,qz), Vector3d(tx,ty,tz)) ref:333-335
+inline SE3d make_pose(double qx, double qy, double qz, double qw, double tx, double ty, double tz) {
+    return SE3d(Eigen::Quaterniond(qw, qx, qy, qz), Eigen::Vector3d(tx, ty, tz));
+}
+// pose_curr_TWC.inverse() * pose_ref_TWC ref:289-290
+inline SE3d relative_pose(const SE3d &T_WC_ref, const SE3d &T_WC_curr) { return T_WC_curr.inverse() * T_WC_ref; }
+inline Mat make_mat64(int rows, int cols) { return Mat(rows, cols, CV_64F); }
 }  // namespace slamplay_b200
 #else
 namespace slamplay_b200 {
@@ -52,6 +63,7 @@ struct Mat {
     size_t step = 0;
     int rows = 0, cols = 0;
     int type_ = kType8UC1;
+    std::shared_ptr<std::vector<unsigned char>> own_;  // set when the Mat owns its pixels (make_mat64, like cv::Mat(rows, cols, type))
     Mat() = default;
     Mat(int r, int c, int type, void *ext, size_t ext_step) : data(static_cast<unsigned char *>(ext)), step(ext_step), rows(r), cols(c), type_(type) {}
     int type() const { return type_; }
@@ -66,6 +78,58 @@ struct SE3d {
 inline void pose_of(const SE3d &T, double q[4], double t[3]) {
     std::memcpy(q, T.q, sizeof(T.q));
     std::memcpy(t, T.t, sizeof(T.t));
+}
+inline Mat make_mat64(int rows, int cols) {
+    Mat m;
+    m.own_ = std::make_shared<std::vector<unsigned char>>(size_t(rows) * cols * sizeof(double));
+    m.data = m.own_->data(); m.step = size_t(cols) * sizeof(double); m.rows = rows; m.cols = cols; m.type_ = kType64F;
+    return m;
+}
+// The Sophus / Eigen arithmetic the reference's driver applies to poses, in the same operation order (so a build
+// without Sophus hands the kernels the same bits): quaternion normalisation of the SE3d constructor
+// (packet reduction (x2+z2)+(y2+w2)), Quaternion::_transformVector, SE3::inverse, SE3 * SE3.
+namespace detail {
+inline void qnormalize(double q[4]) {
+    const double n = std::sqrt((q[0] * q[0] + q[2] * q[2]) + (q[1] * q[1] + q[3] * q[3]));
+    for (int i = 0; i < 4; i++) q[i] /= n;
+}
+inline void cross(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline void rotate(const double q[4], const double v[3], double o[3]) {
+    double uv[3], c[3];
+    cross(q, v, uv);
+    for (int i = 0; i < 3; i++) uv[i] = uv[i] + uv[i];
+    cross(q, uv, c);
+    for (int i = 0; i < 3; i++) o[i] = v[i] + uv[i] * q[3] + c[i];
+}
+}  // namespace detail
+// SE3d(Quaterniond(qw,qx,qy,qz), Vector3d(tx,ty,tz)) ref:333-335 — the constructor normalises the quaternion
+inline SE3d make_pose(double qx, double qy, double qz, double qw, double tx, double ty, double tz) {
+    SE3d T;
+    T.q[0] = qx; T.q[1] = qy; T.q[2] = qz; T.q[3] = qw;
+    detail::qnormalize(T.q);
+    T.t[0] = tx; T.t[1] = ty; T.t[2] = tz;
+    return T;
+}
+// pose_curr_TWC.inverse() * pose_ref_TWC ref:289-290
+inline SE3d relative_pose(const SE3d &T_WC_ref, const SE3d &T_WC_curr) {
+    SE3d inv;  // Sophus SE3::inverse: invR = conj(q) (normalised), t' = invR * (t * -1)
+    inv.q[0] = -T_WC_curr.q[0]; inv.q[1] = -T_WC_curr.q[1]; inv.q[2] = -T_WC_curr.q[2]; inv.q[3] = T_WC_curr.q[3];
+    detail::qnormalize(inv.q);
+    const double nt[3] = {T_WC_curr.t[0] * -1.0, T_WC_curr.t[1] * -1.0, T_WC_curr.t[2] * -1.0};
+    detail::rotate(inv.q, nt, inv.t);
+    SE3d out;  // SE3 * SE3: (R_a R_b (normalised), t_a + R_a t_b)
+    const double *a = inv.q, *b = T_WC_ref.q;
+    out.q[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    out.q[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    out.q[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    out.q[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    detail::qnormalize(out.q);
+    double r[3];
+    detail::rotate(inv.q, T_WC_ref.t, r);
+    for (int i = 0; i < 3; i++) out.t[i] = inv.t[i] + r[i];
+    return out;
 }
 }  // namespace slamplay_b200
 #endif
@@ -84,6 +148,40 @@ namespace slamplay_b200 {
             std::abort();                                                           \
         }                                                                           \
     } while (0)
+
+// readDatasetFiles (ref:317-352): the REMODE test-set layout.
+//   <path>/first_200_frames_traj_over_table_input_sequence.txt   one line per frame: image tx ty tz qx qy qz qw (T_WC)
+//   <path>/images/<image>                                        (ref:332)
+//   <path>/depthmaps/scene_000.depth                             width*height numbers in centimetres (ref:341-349: / 100)
+// Same signature and results as the reference's function, with one deliberate difference: the reference's
+// `while (!fin.eof())` loop appends one bogus entry (empty file name, uninitialised pose) when the list ends with a
+// newline, which its driver then skips because imread fails (ref:288); this reader returns the complete entries only.
+inline bool readDatasetFiles(const std::string &path, std::vector<std::string> &color_image_files, std::vector<SE3d> &poses,
+                             Mat &ref_depth, int width = 640, int height = 480) {
+    std::ifstream fin(path + "/first_200_frames_traj_over_table_input_sequence.txt");
+    if (!fin) return false;
+    for (;;) {
+        std::string image;
+        double d[7];
+        if (!(fin >> image)) break;
+        bool ok = true;
+        for (double &v : d) ok = ok && bool(fin >> v);
+        if (!ok) break;
+        color_image_files.push_back(path + std::string("/images/") + image);
+        poses.push_back(make_pose(d[3], d[4], d[5], d[6], d[0], d[1], d[2]));
+    }
+    fin.close();
+    fin.open(path + "/depthmaps/scene_000.depth");
+    ref_depth = make_mat64(height, width);
+    if (!fin) return false;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            double depth = 0;
+            fin >> depth;
+            ref_depth.template ptr<double>(y)[x] = depth / 100.0;
+        }
+    return true;
+}
 
 // Resident mapper: one context per image geometry / device.
 class DenseMonoMapper {
@@ -121,6 +219,15 @@ public:
         pose_of(T_C_R, q, t);
         if (dmf_update(ctx_, curr.data, curr.step, q, t) != DMF_OK) die("dmf_update", ctx_);
     }
+    // One strict update() (:355): maps read from and valid again in the caller's memory; the reference image is
+    // uploaded only when its content changes, unchanged maps are not uploaded again (dmf_update_strict).
+    void updateStrict(const Mat &ref, const Mat &curr, const SE3d &T_C_R, Mat &depth, Mat &depth_cov2) {
+        check8(ref, "ref"); check8(curr, "curr"); check64(depth, "depth"); check64(depth_cov2, "depth_cov2");
+        double q[4], t[3];
+        pose_of(T_C_R, q, t);
+        if (dmf_update_strict(ctx_, ref.data, ref.step, curr.data, curr.step, q, t, reinterpret_cast<double *>(depth.data), depth.step,
+                              reinterpret_cast<double *>(depth_cov2.data), depth_cov2.step) != DMF_OK) die("dmf_update_strict", ctx_);
+    }
     void download(Mat &depth, Mat &depth_cov2) {
         check64(depth, "depth"); check64(depth_cov2, "depth_cov2");
         if (dmf_download_state(ctx_, reinterpret_cast<double *>(depth.data), depth.step,
@@ -152,11 +259,7 @@ inline void update(const Mat &ref, const Mat &curr, const SE3d &T_C_R, Mat &dept
     auto key = std::make_tuple(ref.cols, ref.rows);
     auto it = cache.find(key);
     if (it == cache.end()) it = cache.emplace(key, std::make_unique<DenseMonoMapper>(ref.cols, ref.rows)).first;
-    DenseMonoMapper &m = *it->second;
-    m.setReference(ref);
-    m.upload(depth, depth_cov2);
-    m.update(curr, T_C_R);
-    m.download(depth, depth_cov2);
+    it->second->updateStrict(ref, curr, T_C_R, depth, depth_cov2);
 }
 
 }  // namespace slamplay_b200

@@ -163,6 +163,16 @@ class DepthFilter:
         self._ck(self._lib.dmf_update_device(self._ctx, C.c_void_p(dev_ptr), step, q, t,
                                              C.c_void_p(wait_stream) if wait_stream else None), "dmf_update_device")
 
+    def update_strict(self, ref: np.ndarray, curr: np.ndarray, T_C_R, depth: np.ndarray, depth_cov2: np.ndarray) -> None:
+        """The reference's update(ref, curr, T_C_R, depth, depth_cov2) in one call (dmf_update_strict): the maps are valid
+        in host memory on return; the reference image and unchanged maps are not uploaded again."""
+        p = self.params
+        ref, curr = _check_u8("ref", ref, p), _check_u8("curr", curr, p)
+        d, c = _check_f64("depth", depth, p), _check_f64("depth_cov2", depth_cov2, p)
+        q, t = _pose_arrays(T_C_R)
+        self._ck(self._lib.dmf_update_strict(self._ctx, ref.ctypes.data, ref.strides[0], curr.ctypes.data, curr.strides[0], q, t,
+                                             d.ctypes.data, d.strides[0], c.ctypes.data, c.strides[0]), "dmf_update_strict")
+
     def update_ring(self, ring, T_C_R) -> None:
         """update() against the next frame of a FrameRing (dmf_update_ring): the frame is pulled into this context's
         buffer by a copy engine, ordered against the producer by stream memory operations; asynchronous."""
@@ -298,10 +308,7 @@ def update(ref: np.ndarray, curr: np.ndarray, T_C_R, depth: np.ndarray, depth_co
     if f is None:
         f = DepthFilter(params, device=device)
         _strict_ctx[key] = f
-    f.set_reference(ref)
-    f.upload_state(depth, depth_cov2)
-    f.update(curr, T_C_R)
-    f.download_state(depth, depth_cov2)
+    f.update_strict(ref, curr, T_C_R, depth, depth_cov2)
 
 
 def release_strict_contexts() -> None:

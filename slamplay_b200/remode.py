@@ -53,8 +53,9 @@ def read_dataset(path: str, width: int = 640, height: int = 480) -> Tuple[List[s
     return files, poses, depth.reshape(height, width) / 100.0
 
 
-def write_dataset(path: str, seq, frames, ref_distance: np.ndarray) -> None:
-    """Writes a synthetic sequence in the REMODE layout (PNG images need cv2)."""
+def write_dataset(path: str, seq, frames, ref_distance: np.ndarray, ext: str = "png") -> None:
+    """Writes a synthetic sequence in the REMODE layout (images through cv2: "png" like the real set, or "pgm" for readers
+    without an image library, e.g. slamplay_b200/cpp/example_remode_dir.cpp)."""
     import cv2
 
     root = Path(path)
@@ -62,7 +63,7 @@ def write_dataset(path: str, seq, frames, ref_distance: np.ndarray) -> None:
     os.makedirs(root / "depthmaps", exist_ok=True)
     with open(root / POSE_FILE, "w") as f:
         for i, (img, T) in enumerate(zip(frames, seq.poses_T_WC)):
-            name = f"scene_{i:03d}.png"
+            name = f"scene_{i:03d}.{ext}"
             cv2.imwrite(str(root / "images" / name), img)
             q, t = T.q, T.t
             f.write(f"{name} {t[0]!r} {t[1]!r} {t[2]!r} {q[0]!r} {q[1]!r} {q[2]!r} {q[3]!r}\n")

@@ -3,7 +3,7 @@
 A sequence = scene + intrinsics + a list of camera poses T_WC (frame 0 is the reference frame,
 like the REMODE list read at dense_mapping/test_monocular_mapping.cpp:322-337) and is rendered
 either on the CPU (libdmf_synth_cpu.so, for the CPU test-suite and golden fixtures) or on the
-GPU (libdmf.so, for the 1080p / 4K benchmark sequences).  Both renderers are bit-identical.
+GPU (libdmf_synth.so, for the 1080p / 4K benchmark sequences).  Both renderers are bit-identical.
 """
 from __future__ import annotations
 
@@ -83,7 +83,7 @@ class Sequence:
     # -- GPU rendering (into caller-provided device memory) ------------------------------
     def render_device(self, i: int, img_ptr: int, pitch: int, dist_ptr: int = 0, dist_pitch: int = 0,
                       stream: int = 0) -> None:
-        lib = _lib.load_dmf()
+        lib = _lib.load_synth_cuda()
         cam = self.camera(i)
         rc = lib.dmf_synth_render_device(C.byref(self.scene), C.byref(cam), C.c_void_p(img_ptr), pitch,
                                          C.c_void_p(dist_ptr) if dist_ptr else None, dist_pitch,

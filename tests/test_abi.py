@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, s), f"libdmf.so does not export {s}"
         assert s in _lib.DMF_SYMBOLS, f"{s} has no ctypes signature in slamplay_b200/_lib.py"
     for s in declared_symbols(ROOT / "include" / "dmf_synth.h"):
-        owner = _lib.load_synth_cpu() if s.endswith("_host") else lib
+        owner = _lib.load_synth_cpu() if s.endswith("_host") else _lib.load_synth_cuda()
         assert hasattr(owner, s), f"{s} is not exported"
 
 

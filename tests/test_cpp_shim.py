@@ -39,3 +39,80 @@ def test_example_driver_runs(tmp_path):
     n_last = int(re.search(r"cov2 < 0.5: (\d+)", lines[-1]).group(1))
     mean = float(re.search(r"mean depth ([0-9.]+)", lines[-1]).group(1))
     assert n_last > 50000 and 1.7 < mean < 2.6
+
+
+def _build_remode_example(tmp_path):
+    exe = tmp_path / "example_remode_dir"
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", str(PKG / "cpp" / "example_remode_dir.cpp"), "-o", str(exe),
+           f"-L{PKG}", "-ldmf", f"-Wl,-rpath,{PKG}", "-L/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _write_remode_dir(tmp_path, n_frames):
+    from slamplay_b200.remode import write_dataset
+    from slamplay_b200.synth import make_sequence
+    seq = make_sequence("remode_640x480", n_frames=n_frames)
+    frames = [seq.render_host(i) for i in range(n_frames)]
+    _, gt = seq.render_host(0, with_distance=True)
+    d = tmp_path / "remode"
+    write_dataset(str(d), seq, frames, gt, ext="pgm")
+    return seq, frames, gt, d
+
+
+def test_cpp_reader_and_pose_chain_equal_the_compiled_reference(tmp_path):
+    """readDatasetFiles (ref:317-352) and T_C_R = T_WC(i)^-1 * T_WC(0) (ref:289-290) of the header-only shim (no Sophus,
+    no OpenCV) against the reference's own reader / Sophus stand-in compiled from the unmodified TU: same bits."""
+    import numpy as np
+
+    import oracle
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref/libdmf_ref.so not built (no /root/reference here)")
+    seq, frames, gt, d = _write_remode_dir(tmp_path, 4)
+    exe = _build_remode_example(tmp_path)
+    r = subprocess.run([str(exe), str(d), "--dump-poses"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    files_ref, poses_ref, depth_ref = oracle.ref_read_dataset(str(d))
+    lines = [l for l in r.stdout.splitlines() if l.startswith("pose ")]
+    assert len(lines) == 4 and len(files_ref) in (4, 5)
+    for k, line in enumerate(lines):
+        left, right = line.split("|")
+        got = [float.fromhex(v) for v in left.split()[2:]]
+        rel = [float.fromhex(v) for v in right.split()[1:]]
+        assert got == list(poses_ref[k]), k
+        assert rel == list(oracle.ref_compose_T_C_R(poses_ref[0], poses_ref[k])), k
+    dl = [l for l in r.stdout.splitlines() if l.startswith("ref_depth")][0].split()
+    assert float.fromhex(dl[4]) == depth_ref[0, 0] and float.fromhex(dl[6]) == depth_ref[-1, -1]
+    s = 0.0
+    for v in depth_ref.reshape(-1):
+        s += v
+    assert float.fromhex(dl[2]) == s
+
+
+@pytest.mark.gpu
+def test_remode_directory_driver_runs_end_to_end(tmp_path):
+    """The reference's whole driver loop (ref:253-310) on a written REMODE-layout directory through the shim: reader,
+    pose chain, strict update(), evaludateDepth — against the Python path on the same inputs."""
+    import numpy as np
+
+    from slamplay_b200.depth_filter import DepthFilter
+    seq, frames, gt, d = _write_remode_dir(tmp_path, 8)
+    exe = _build_remode_example(tmp_path)
+    r = subprocess.run([str(exe), str(d)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rms = [l for l in r.stdout.splitlines() if l.startswith("Average error (RMS)")]
+    assert len(rms) == 7
+    f = DepthFilter(seq.params)
+    f.set_reference(frames[0])
+    f.fill_state(3.0, 3.0)
+    for i in range(1, 8):
+        f.update(frames[i], seq.T_C_R(i))
+    dep, cov = f.download_state()
+    f.close()
+    good = cov[20:-20, 20:-20] < 2e-4
+    want = float(np.sqrt(((gt[20:-20, 20:-20] - dep[20:-20, 20:-20])[good] ** 2).mean())) if good.any() else 0.0
+    got = float(re.search(r"= ([0-9.e+-]+) over (\d+)", rms[-1]).group(1))
+    n = int(re.search(r"over (\d+) pixels", rms[-1]).group(1))
+    assert n == int(good.sum())
+    assert abs(got - want) <= 1e-8 * max(want, 1e-12)

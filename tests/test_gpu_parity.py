@@ -560,3 +560,31 @@ def test_inverse_depth_variant_against_reference_fixture(DF):
     assert depth_agreement(p, d, d_ref, rows) >= MIN_DEPTH_AGREE
     assert depth_agreement(p, d, d_ref, rows, rtol=1e-6) > 0.999
     assert class_mismatch(p, c, c_ref, rows) <= MAX_DECISION_MISMATCH
+
+
+def test_strict_dropin_caches_are_transparent(DF, seq640):
+    """dmf_update_strict skips re-uploading an unchanged reference image / unchanged maps.  Neither cache may be
+    observable: the caller edits the maps between calls, swaps the reference image for another one and back, and passes
+    copies at new addresses — every call must equal the oracle's update() on the same arguments."""
+    from slamplay_b200.depth_filter import release_strict_contexts, update
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    depth, cov2 = np.full((h, w), 3.0), np.full((h, w), 3.0)
+    d_ref, c_ref = depth.copy(), cov2.copy()
+    plan = [(0, 1, None), (0, 2, None), (0, 3, "edit"), (1, 4, None), (0, 5, "copy"), (0, 2, "edit")]
+    for ref_i, cur_i, action in plan:
+        if action == "edit":      # the caller overwrites part of the state between two calls
+            for m in (depth, d_ref):
+                m[100:140, 200:300] = 2.5
+            for m in (cov2, c_ref):
+                m[100:140, 200:300] = 1.0
+        if action == "copy":      # same contents at new addresses
+            depth, cov2 = depth.copy(), cov2.copy()
+        ref_img = frames[ref_i].copy() if action == "copy" else frames[ref_i]
+        T = seq.T_C_R(cur_i)
+        update(ref_img, frames[cur_i], T, depth, cov2)
+        oracle.update(p, frames[ref_i], frames[cur_i], T.q, T.t, d_ref, c_ref)
+        assert depth_agreement(p, depth, d_ref, rtol=1e-6) > 0.9999, (ref_i, cur_i, action)
+        assert class_mismatch(p, cov2, c_ref) <= MAX_DECISION_MISMATCH
+    release_strict_contexts()
