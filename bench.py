@@ -486,7 +486,8 @@ def ours(args) -> dict | None:
     if world > 1 and not args.no_parity:
         gathered = one_step()
         if rank == 0:
-            result["parity_sample"] = multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, local_rank)
+            result["parity_sample"] = multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, local_rank,
+                                                       {k: cnt[k] // args.steps for k in ("interior", "active", "ncc_evals", "accepted")})
         dist.barrier()
 
     # ---- CPU baseline (rank 0, N == 1 only) + parity on the sampled rows -------------------
@@ -666,8 +667,9 @@ def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, pos
             "api": f"ShardedDepthFilter.update_host (pinned host frames on rank 0 -> {sf.transport}) + gather_state + D2H"}
 
 
-def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_index) -> dict:
-    """Rank 0: the same sequence on ONE context; SHA-256 and bitwise comparison with the maps gathered from N ranks."""
+def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_index, counters_n) -> dict:
+    """Rank 0: the same sequence on ONE context; SHA-256 and bitwise comparison with the maps gathered from N ranks, and
+    the work counters of one step summed over the ranks against the single context's."""
     import hashlib
 
     from slamplay_b200.depth_filter import DepthFilter
@@ -681,6 +683,7 @@ def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_inde
     for i in range(1, seq.n_frames):
         f.update_device(frames[i].data_ptr(), pitch, poses_all[i], wait_stream=s)
     single = f.download_state()
+    c1 = f.counters()
     f.close()
     b = seq.params.border
     I = (slice(b, h - b), slice(b, w - b))
@@ -689,7 +692,9 @@ def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_inde
     return {"against": "the same sequence on one GPU (rank 0), all interior pixels",
             "sha256_depth": sha(multi[0][I]), "sha256_depth_1gpu": sha(single[0][I]),
             "sha256_cov2": sha(multi[1][I]), "sha256_cov2_1gpu": sha(single[1][I]),
-            "bit_identical": bool(same[0] == 1.0 and same[1] == 1.0), "bitwise_equal_frac": {"depth": same[0], "cov2": same[1]}}
+            "bit_identical": bool(same[0] == 1.0 and same[1] == 1.0), "bitwise_equal_frac": {"depth": same[0], "cov2": same[1]},
+            "work_counters_equal": all(int(counters_n[k]) == int(c1[k]) for k in counters_n),
+            "work_counters": {"n_gpus": counters_n, "one_gpu": {k: c1[k] for k in counters_n}}}
 
 
 def cpu_baseline_and_parity(args, seq, frames, sf, torch, target_ncc: float) -> dict:

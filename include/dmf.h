@@ -210,6 +210,13 @@ int dmf_download_debug(dmf_ctx *ctx, float *best_ncc_host, int32_t *samples_host
 int dmf_device_state(dmf_ctx *ctx, double **depth_dev, double **cov2_dev, size_t *pitch);
 int dmf_stream(dmf_ctx *ctx, void **stream);
 
+/*
+ * Device self-test: the kernels compute groups of IEEE-rounded FP64 quotients over one denominator with a shared
+ * reciprocal (slamplay_b200/csrc/dmf_geometry.h quo2 / quo3).  Compares `n` pseudo-random groups (normal, huge, tiny,
+ * zero, infinite, NaN and denormal operands) with __ddiv_rn bit for bit; *mismatches must come back 0.
+ */
+int dmf_selftest_division(int device, uint64_t n, uint64_t seed, uint64_t *mismatches);
+
 /* Pinned host memory helpers for zero-staging dmf_update() calls. */
 int dmf_alloc_pinned(void **ptr, size_t bytes);
 int dmf_free_pinned(void *ptr);

@@ -97,6 +97,7 @@ DMF_SYMBOLS = {
     "dmf_download_debug": (C.c_int, [_vp, _vp, _vp]),
     "dmf_device_state": (C.c_int, [_vp, _P(_vp), _P(_vp), _P(C.c_size_t)]),
     "dmf_stream": (C.c_int, [_vp, _P(_vp)]),
+    "dmf_selftest_division": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
     "dmf_alloc_pinned": (C.c_int, [_P(_vp), C.c_size_t]),
     "dmf_free_pinned": (C.c_int, [_vp]),
     "dmf_set_truth": (C.c_int, [_vp, _vp, C.c_size_t]),

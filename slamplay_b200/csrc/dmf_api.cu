@@ -356,9 +356,15 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             return rc_;                                                                                   \
         }                                                                                                 \
     } while (0)
-    CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUX(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CUX(cudaStreamCreateWithFlags(&c->mom_stream, cudaStreamNonBlocking));
+    {
+        // the frame copy and the frame-only precompute of the NEXT update run beside the persistent ncc_kernel of the
+        // current one: give them the higher priority so that their CTAs are placed first whenever an SM has room
+        int prio_lo = 0, prio_hi = 0;
+        CUX(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUX(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+        CUX(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi));
+        CUX(cudaStreamCreateWithPriority(&c->mom_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CUX(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
     const size_t img_bytes = (size_t)c->img_pitch * H;
     CUX(cudaMalloc(&c->d_ref, img_bytes));
@@ -802,6 +808,21 @@ int dmf_device_state(dmf_ctx *c, double **depth_dev, double **cov2_dev, size_t *
 int dmf_stream(dmf_ctx *c, void **stream) {
     if (!c || !stream) return fail(c, DMF_ERR_INVALID, "dmf_stream: NULL argument");
     *stream = (void *)c->stream;
+    return DMF_OK;
+}
+
+int dmf_selftest_division(int device, uint64_t n, uint64_t seed, uint64_t *mismatches) {
+    dmf_ctx_impl *c = nullptr;
+    if (!mismatches) return fail(c, DMF_ERR_INVALID, "dmf_selftest_division: NULL argument");
+    CU(cudaSetDevice(device));
+    unsigned long long *d = nullptr, h = 0;
+    CU(cudaMalloc(&d, sizeof(h)));
+    CU(cudaMemset(d, 0, sizeof(h)));
+    dmf::division_selftest_kernel<<<148 * 8, 256>>>((unsigned long long)seed, (unsigned long long)n, d);
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, DMF_ERR_CUDA, std::string("dmf_selftest_division: ") + cudaGetErrorString(e));
+    *mismatches = h;
     return DMF_OK;
 }
 

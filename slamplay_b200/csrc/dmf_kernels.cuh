@@ -727,7 +727,13 @@ __global__ void __launch_bounds__(TILE_PIX, DMF_FUSE_MIN_BLOCKS) fuse_kernel(con
 // update k can be active in update k+1.  The fused state goes from registers straight into the next search geometry;
 // the maps are written but not read, and the converged / diverged pixels cost nothing any more.  P.q/P.t: pose of
 // update k+1 (setup part); P.qi/P.ti/P.ti_norm: inverse pose of update k (fusion part).
-__global__ void __launch_bounds__(TILE_PIX) advance_kernel(const __grid_constant__ KParams P) {
+// 4 CTAs of 256 threads per SM (64 registers): the kernel is a long chain of dependent FP64 operations (IEEE divisions
+// and square roots in the reference's order), i.e. latency-bound: measured 37.0 ms per 1080p step at 2 CTAs / SM (84
+// registers), 28.3 at 3, 24.1 at 4, 23.5 at 5 (profiles/r02_ab_advance_kernel.txt)
+#ifndef DMF_ADV_MIN_BLOCKS
+#define DMF_ADV_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TILE_PIX, DMF_ADV_MIN_BLOCKS) advance_kernel(const __grid_constant__ KParams P) {
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
     if (cta == 0 && threadIdx.x < sizeof(Ctrl) / sizeof(unsigned)) reinterpret_cast<unsigned *>(P.ctrl_zero)[threadIdx.x] = 0;
     const unsigned n_fin = P.cta_fin[cta];
@@ -745,6 +751,41 @@ __global__ void __launch_bounds__(TILE_PIX) advance_kernel(const __grid_constant
     }
     prepare_pixel(P, w, have);
     emit_pixel(P, w, accepted, n_fin);
+}
+
+// ----------------------------------------------------------------------------------------
+// Self-test of the grouped divisions of dmf_geometry.h (quo2 / quo3: shared reciprocal, one range test per group)
+// against __ddiv_rn on pseudo-random operands: exponents from 2^-140 to 2^140 (beyond the fast range on both sides),
+// plus zeros, infinities, NaNs and denormals.  Counts quotients whose bits differ (NaN matches NaN).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h;
+}
+__device__ __forceinline__ double test_operand(unsigned long long h) {
+    const unsigned sel = (unsigned)(h >> 58);  // 6 bits
+    if (sel == 0) return 0.0;
+    if (sel == 1) return __longlong_as_double(0x7ff0000000000000ll);                      // inf
+    if (sel == 2) return __longlong_as_double(0x7ff8000000000000ll);                      // NaN
+    if (sel == 3) return __longlong_as_double((long long)(h & 0x000fffffffffffffull));    // denormal
+    const long long e = 1023 - 140 + (long long)((h >> 40) % 281);
+    const unsigned long long sign = (h >> 57) & 1ull;
+    return __longlong_as_double((long long)((sign << 63) | ((unsigned long long)e << 52) | (h & 0x000fffffffffffffull)));
+}
+__device__ __forceinline__ bool same_bits(double a, double b) {
+    return (a != a && b != b) || __double_as_longlong(a) == __double_as_longlong(b);
+}
+__global__ void __launch_bounds__(256) division_selftest_kernel(unsigned long long seed, unsigned long long n, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = mix64(seed + i * 0x9e3779b97f4a7c15ull);
+        const double b = test_operand(mix64(h ^ 1)), a0 = test_operand(mix64(h ^ 2)), a1 = test_operand(mix64(h ^ 3)), a2 = test_operand(mix64(h ^ 4));
+        double q0, q1, q2, p0, p1;
+        dmf_geom::quo3(a0, a1, a2, b, q0, q1, q2);
+        dmf_geom::quo2(a1, a2, b, p0, p1);
+        bad += !same_bits(q0, __ddiv_rn(a0, b)) + !same_bits(q1, __ddiv_rn(a1, b)) + !same_bits(q2, __ddiv_rn(a2, b)) +
+               !same_bits(p0, __ddiv_rn(a1, b)) + !same_bits(p1, __ddiv_rn(a2, b));
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // ----------------------------------------------------------------------------------------

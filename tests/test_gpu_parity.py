@@ -588,3 +588,13 @@ def test_strict_dropin_caches_are_transparent(DF, seq640):
         assert depth_agreement(p, depth, d_ref, rtol=1e-6) > 0.9999, (ref_i, cur_i, action)
         assert class_mismatch(p, cov2, c_ref) <= MAX_DECISION_MISMATCH
     release_strict_contexts()
+
+
+def test_grouped_divisions_are_bit_identical_to_ieee_division():
+    """dmf_geometry.h computes groups of quotients over one denominator with a shared reciprocal; on the device every
+    quotient must carry the bits of __ddiv_rn (the host build of the same header, which the CPU suite pins to the
+    oracle, uses plain IEEE division)."""
+    from slamplay_b200 import _lib
+    bad = C.c_uint64(123)
+    assert _lib.load_dmf().dmf_selftest_division(0, 200_000_000, 20261017, C.byref(bad)) == 0
+    assert bad.value == 0

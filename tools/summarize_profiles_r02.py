@@ -69,7 +69,7 @@ for wl in ("hd_1920x1080", "uhd_3840x2160"):
         "pipe_lsu_per_eval": d["sm__inst_executed_pipe_lsu.sum"][0] / ev,
         "lsu_wavefronts_per_eval": d["l1tex__data_pipe_lsu_wavefronts.sum"][0] / ev,
         "dram_bytes_per_launch": byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum"),
-        "under_ncu": {"duration_us": d["gpu__time_duration.sum"][0], "lsu_wavefronts_pct_of_peak": d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0],
+        "under_ncu": {"duration_us": d["gpu__time_duration.sum"][0] * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(d["gpu__time_duration.sum"][1], 1.0), "lsu_wavefronts_pct_of_peak": d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0],
                       "issue_active_pct": d["sm__inst_issued.avg.pct_of_peak_sustained_active"][0], "warps_active_pct": d["sm__warps_active.avg.pct_of_peak_sustained_active"][0],
                       "l1_hit_pct": d["l1tex__t_sector_hit_rate.pct"][0], "l2_hit_pct": d["lts__t_sector_hit_rate.pct"][0],
                       "registers_per_thread": d["launch__registers_per_thread"][0]},
