@@ -240,8 +240,12 @@ def reference_arm(args) -> dict:
             times.append(dt)
     t = sum(times) / len(times)
     value = cnts["interior"] / t
+    try:  # hygiene: which of this repository's native libraries this process has mapped (the product libdmf.so must not be one)
+        loaded = sorted({Path(l.split()[-1]).name for l in open("/proc/self/maps") if str(ROOT) in l and ".so" in l})
+    except OSError:
+        loaded = None
     return {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "native_libs_loaded": loaded, "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "width": w, "height": h, "frames": seq.n_frames, "sample": sample},

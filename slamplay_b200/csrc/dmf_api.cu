@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,9 +61,13 @@ struct dmf_ctx_impl {
     uint2 *d_currx[2] = {nullptr, nullptr};
     cudaEvent_t ev_mom_done[2] = {nullptr, nullptr};  // moments_kernel wrote table b (mom_stream)
     cudaEvent_t ev_tab_free[2] = {nullptr, nullptr};  // ncc_kernel that read table b finished (stream)
+    cudaEvent_t ev_adv_done[2] = {nullptr, nullptr};  // advance / setup kernel of update u finished (stream), by parity of u
+    bool mom_gate = true;                             // moments(u) is released with ncc(u-1), not earlier (DMF_MOMENTS_GATE=0: off)
     cudaEvent_t ev_frame = nullptr;                   // the frame of this update is complete in HBM
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
+    bool mom_bulk = true;                      // moments_bulk_kernel (DMF_MOMENTS=legacy selects moments_kernel: A/B runs)
+    int mom_grid = 296;                        // persistent CTAs of moments_bulk_kernel (DMF_MOMENTS_CTAS_PER_SM x SMs)
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
     // optional per-kernel timing (dmf_set_timing): 5 events per update bracket the 4 timing slots
     bool timing_on = false;
@@ -208,12 +213,29 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         // is serialised on the context stream so that the event pairs bracket one kernel each.
         cudaStream_t ms = c->timing_on ? c->stream : c->mom_stream;
         if (frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));
-        if (ms != c->stream) CU(cudaStreamWaitEvent(ms, c->ev_tab_free[b], 0));  // ncc_kernel of two updates ago
+        if (ms != c->stream) {
+            CU(cudaStreamWaitEvent(ms, c->ev_tab_free[b], 0));  // ncc_kernel of two updates ago has released the table buffer
+            // ... and not before the ncc_kernel of the PREVIOUS update is released: beside advance_kernel (which fills every
+            // register file) the precompute would only take its place in the queue; beside ncc_kernel it runs in the
+            // registers that kernel leaves free
+            if (c->mom_gate && u > 0) CU(cudaStreamWaitEvent(ms, c->ev_adv_done[b ^ 1], 0));
+        }
         if (ev[0]) CU(cudaEventRecord(ev[0], c->stream));
         if (merged) dmf::advance_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);  // fusion of u-1 + setup of u
         else dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
-        dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
+        CU(cudaEventRecord(c->ev_adv_done[b], c->stream));
+        if (c->mom_bulk && (reinterpret_cast<uintptr_t>(d_curr) & 15u) == 0 && (curr_pitch & 15) == 0) {
+            // tiles staged in shared memory by bulk asynchronous copies: efficient at the one-CTA-per-SM occupancy that is
+            // left beside the persistent ncc_kernel of the previous update
+            const int tiles_x = (p.width - 15 + dmf::MB_COLS - 1) / dmf::MB_COLS, tiles_y = (p.height - 8 + dmf::MB_ROWS - 1) / dmf::MB_ROWS;
+            const int n_tiles = tiles_x * tiles_y;
+            const int grid_b = n_tiles < c->mom_grid ? n_tiles : c->mom_grid;
+            dmf::moments_bulk_kernel<<<grid_b, dmf::MB_COLS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width,
+                                                                      c->d_currx[b], tiles_x, n_tiles);
+        } else {
+            dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
+        }
         if (frame_consumed) CU(cudaEventRecord(frame_consumed, ms));
         if (ms != c->stream) {
             CU(cudaEventRecord(c->ev_mom_done[b], ms));
@@ -357,13 +379,14 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         }                                                                                                 \
     } while (0)
     {
-        // the frame copy and the frame-only precompute of the NEXT update run beside the persistent ncc_kernel of the
-        // current one: give them the higher priority so that their CTAs are placed first whenever an SM has room
+        // The frame-only precompute of the NEXT update is released together with the persistent ncc_kernel of the current
+        // one (see launch_update) and must only fill the room ncc_kernel leaves (one small CTA per SM): the context
+        // stream gets the higher priority, so that all ncc_kernel CTAs are placed first.
         int prio_lo = 0, prio_hi = 0;
         CUX(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUX(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+        CUX(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
         CUX(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi));
-        CUX(cudaStreamCreateWithPriority(&c->mom_stream, cudaStreamNonBlocking, prio_hi));
+        CUX(cudaStreamCreateWithPriority(&c->mom_stream, cudaStreamNonBlocking, prio_lo));
     }
     CUX(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
     const size_t img_bytes = (size_t)c->img_pitch * H;
@@ -420,6 +443,7 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             CUX(cudaMemsetAsync(c->d_currx[b], 0, W * H * sizeof(uint2), c->stream));
             CUX(cudaEventCreateWithFlags(&c->ev_mom_done[b], cudaEventDisableTiming));
             CUX(cudaEventCreateWithFlags(&c->ev_tab_free[b], cudaEventDisableTiming));
+            CUX(cudaEventCreateWithFlags(&c->ev_adv_done[b], cudaEventDisableTiming));
         }
         CUX(cudaMalloc(&c->d_refx, W * H * sizeof(uint2)));
         CUX(cudaMemsetAsync(c->d_refx, 0, W * H * sizeof(uint2), c->stream));
@@ -434,9 +458,32 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             case 3840: c->ncc_fn = dmf::ncc_kernel<3840>; break;
             default: c->ncc_fn = dmf::ncc_kernel<0>; break;
         }
+        {
+            // Kernels that are to share an SM must agree on its L1 / shared-memory split: ncc_kernel uses no shared memory,
+            // moments_bulk_kernel stages its tiles there; with different carve-outs the second kernel's CTAs wait until
+            // the SM has drained (measured: no overlap at all).  Both ask for the same 32 KB-class carve-out.
+            const char *cv = std::getenv("DMF_SMEM_CARVEOUT");
+            const int carve = cv ? std::atoi(cv) : 14;
+            if (carve >= 0) {
+                CUX(cudaFuncSetAttribute(c->ncc_fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                CUX(cudaFuncSetAttribute(dmf::moments_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            }
+        }
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ncc_fn, dmf::NCC_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         c->ncc_grid = prop.multiProcessorCount * per_sm;  // persistent CTAs: one resident wave
+        {
+            const char *mm = std::getenv("DMF_MOMENTS"), *mc = std::getenv("DMF_MOMENTS_CTAS_PER_SM");
+            // moments_bulk_kernel (tiles staged by bulk asynchronous copies) for frames with enough tiles to feed every SM
+            // (>= 1 M pixels: 2 tiles per SM); the per-column kernel for small frames.  Both write the same bits; measured
+            // equal at 1080p / 4K (profiles/r02_ab_ncc_prefetch_and_moments.txt), the per-column kernel 3 % ahead at 640x480.
+            c->mom_bulk = mm ? std::strcmp(mm, "legacy") != 0 : (size_t)params->width * params->height >= (1u << 20);
+            const char *mg = std::getenv("DMF_MOMENTS_GATE");
+            c->mom_gate = !(mg && std::strcmp(mg, "0") == 0);
+            int k = mc ? std::atoi(mc) : 2;
+            if (k < 1) k = 1;
+            c->mom_grid = prop.multiProcessorCount * k;
+        }
     }
     CUX(cudaStreamSynchronize(c->stream));
 #undef CUX
@@ -486,6 +533,7 @@ void dmf_destroy(dmf_ctx *ctx) {
         cudaFree(ctx->d_mom1[b]); cudaFree(ctx->d_mom2[b]); cudaFree(ctx->d_currx[b]);
         if (ctx->ev_mom_done[b]) cudaEventDestroy(ctx->ev_mom_done[b]);
         if (ctx->ev_tab_free[b]) cudaEventDestroy(ctx->ev_tab_free[b]);
+        if (ctx->ev_adv_done[b]) cudaEventDestroy(ctx->ev_adv_done[b]);
     }
     if (ctx->ev_frame) cudaEventDestroy(ctx->ev_frame);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_mask); cudaFree(ctx->d_counters); cudaFree(ctx->d_eval);
@@ -607,7 +655,10 @@ int dmf_update(dmf_ctx *c, const uint8_t *curr_host, size_t step, const double q
     }
     // the device buffer b is free once the kernel of two frames ago has consumed it
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
-    CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, src, src_step, W, H, cudaMemcpyHostToDevice, c->copy_stream));
+    if (src_step == (size_t)c->img_pitch && (size_t)W == src_step)  // contiguous frame: one linear DMA instead of H row descriptors
+        CU(cudaMemcpyAsync(c->d_curr[b], src, src_step * (size_t)H, cudaMemcpyHostToDevice, c->copy_stream));
+    else
+        CU(cudaMemcpy2DAsync(c->d_curr[b], c->img_pitch, src, src_step, W, H, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
     return launch_update(c, c->d_curr[b], c->img_pitch, q, t, c->ev_copied[b], c->ev_consumed[b]);
 }

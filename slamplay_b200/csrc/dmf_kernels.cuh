@@ -362,9 +362,13 @@ constexpr int MOM_STRIP = DMF_MOM_STRIP;
 constexpr int MOM_THREADS = DMF_MOM_THREADS;
 
 struct RowBytes { uint32_t x0l, x0h, x1l, x1h, hi; };  // columns 0..6 (x0) and 1..7 (x1) of one block row; hi = bytes 4..7
+// SMEM: the row lives in shared memory (moments_bulk_kernel) instead of global memory
+template <bool SMEM>
 __device__ __forceinline__ RowBytes load_row_bytes(const uint32_t *wp, unsigned sh) {
-    uint32_t lo, hi;
-    load_row8(wp, sh, lo, hi);
+    uint32_t w0, w1, w2;
+    if (SMEM) { w0 = wp[0]; w1 = wp[1]; w2 = wp[2]; }
+    else { w0 = __ldg(wp); w1 = __ldg(wp + 1); w2 = __ldg(wp + 2); }
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     return {lo, hi & 0x00FFFFFFu, __funnelshift_r(lo, hi, 8), hi >> 8, hi};
 }
 struct RowSums { int s0, s1, q, h; };  // one row: sum cols 0..6, sum cols 1..7, sum of squares cols 0..6, neighbour products
@@ -379,34 +383,26 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
             dp4(a.x1l, b.x0l, dp4(a.x1h, b.x0h, 0))};
 }
 
-__global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
-                                                      int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                      uint2 *__restrict__ currx) {
-    const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
-    const int y0 = blockIdx.y * MOM_STRIP;
-    const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
-    if (x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
-
-    const uint8_t *base = img + (size_t)y0 * pitch + x;
-    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(base - (sh >> 3));
-    const int pw = pitch >> 2;
-
+// One column x, positions y0 .. y_end-1: wp = the 4-byte aligned word that holds byte (x, y0), pw = words per row,
+// sh = 8 * (byte offset of x inside that word).  Rows up to min(y_end + 8, height - 1) are read.
+template <bool SMEM>
+__device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsigned sh, int x, int y0, int y_end, int width, int height,
+                                              int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch, uint2 *__restrict__ currx) {
     // window state for position y0: single-row sums over rows y0..y0+6, pair sums over (y0,y0+1)..(y0+6,y0+7)
     int S0 = 0, S1 = 0, Q = 0, H = 0, V = 0, D1 = 0, D2 = 0;
-    RowBytes prev = load_row_bytes(wp, sh);
+    RowBytes prev = load_row_bytes<SMEM>(wp, sh);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
-        const RowBytes next = load_row_bytes(wp + (j + 1) * pw, sh);
+        const RowBytes next = load_row_bytes<SMEM>(wp + (j + 1) * pw, sh);
         const RowSums r = row_sums(prev);
         const PairSums p = pair_sums(prev, next);
         S0 += r.s0; S1 += r.s1; Q += r.q; H += r.h; V += p.v; D1 += p.d1; D2 += p.d2;
         prev = next;
     }
     // sliding: rows leaving (old_a = y, old_b = y+1) and entering (new_a = y+7, new_b = y+8)
-    RowBytes old_a = load_row_bytes(wp, sh), old_b = load_row_bytes(wp + pw, sh);
+    RowBytes old_a = load_row_bytes<SMEM>(wp, sh), old_b = load_row_bytes<SMEM>(wp + pw, sh);
     RowBytes new_a = prev;  // row y0+7
-    RowBytes new_b = load_row_bytes(wp + 8 * pw, sh);
+    RowBytes new_b = load_row_bytes<SMEM>(wp + 8 * pw, sh);
     for (int y = y0; y < y_end; ++y) {
         const RowSums ro = row_sums(old_a), rn = row_sums(new_a);
         const PairSums po = pair_sums(old_a, old_b), pn = pair_sums(new_a, new_b);
@@ -421,7 +417,7 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
         mom2[(size_t)y * mom_pitch + x] = bx + by;  // |bx|, |by| < 2^30: exact
         // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
         // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
-        // funnel shifts (the 8x larger frame stays L2-resident: 16.6 MB at 1080p)
+        // funnel shifts
         currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
         // advance the window to position y+1
         S0 = S0n; S1 = S1n;
@@ -429,8 +425,91 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__r
         V += pn.v - po.v; D1 += pn.d1 - po.d1; D2 += pn.d2 - po.d2;
         old_a = old_b; new_a = new_b;
         const int yn = y + 1;
-        old_b = load_row_bytes(wp + (size_t)(yn + 1 - y0) * pw, sh);
-        new_b = load_row_bytes(wp + (size_t)(min(yn + 8, height - 1) - y0) * pw, sh);
+        old_b = load_row_bytes<SMEM>(wp + (size_t)(yn + 1 - y0) * pw, sh);
+        new_b = load_row_bytes<SMEM>(wp + (size_t)(min(yn + 8, height - 1) - y0) * pw, sh);
+    }
+}
+
+__global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
+                                                      int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
+                                                      uint2 *__restrict__ currx) {
+    const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
+    const int y0 = blockIdx.y * MOM_STRIP;
+    const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
+    if (x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
+    const uint8_t *base = img + (size_t)y0 * pitch + x;
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
+    moments_strip<false>(reinterpret_cast<const uint32_t *>(base - (sh >> 3)), pitch >> 2, sh, x, y0, y_end, width, height, mom1, mom2,
+                         mom_pitch, currx);
+}
+
+// The same table from tiles staged in SHARED MEMORY by bulk asynchronous copies (cp.async.bulk + mbarrier, the TMA
+// engine; sm_90+).  Why: this kernel is meant to run BESIDE the persistent ncc_kernel of the previous update, which
+// leaves room for one small CTA per SM.  At that occupancy moments_kernel above is latency-bound (every row of the
+// sliding window is a dependent global load): ~10x slower than alone, too slow to finish behind an ncc_kernel of an
+// 8-GPU run (235 us per update at 4K), so the precompute landed on the critical path (26 ms of a 160 ms step).  Here
+// one thread arms an mbarrier and issues one bulk copy per image row of the NEXT tile while the CTA computes the
+// current tile from shared memory: the memory latency is paid once per tile and hidden by the double buffer, whatever
+// the occupancy.  A tile = MB_COLS columns x MB_ROWS positions (+9 halo rows, +16 halo bytes); CTAs are persistent
+// over the tiles.  Needs 16-byte aligned rows (pointer and pitch); dmf_api.cu falls back to moments_kernel otherwise.
+constexpr int MB_COLS = 128, MB_ROWS = 32, MB_TILE_ROWS = MB_ROWS + 9, MB_ROWB = MB_COLS + 16, MB_STAGES = 2;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+__global__ void __launch_bounds__(MB_COLS) moments_bulk_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
+                                                                int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
+                                                                uint2 *__restrict__ currx, int tiles_x, int n_tiles) {
+    __shared__ __align__(16) uint8_t tile[MB_STAGES][MB_TILE_ROWS * MB_ROWB];
+    __shared__ __align__(8) uint64_t bar[MB_STAGES];
+    const int tx = threadIdx.x;
+    if (tx == 0) {
+        for (int s = 0; s < MB_STAGES; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0: arm the stage's barrier with the byte count of the tile and issue one bulk copy per image row
+    auto issue = [&](int t, int s) {
+        const int x0 = (t % tiles_x) * MB_COLS, y0 = (t / tiles_x) * MB_ROWS;
+        const int rows = min(MB_TILE_ROWS, height - y0);
+        const unsigned rb = (unsigned)min(MB_ROWB, pitch - x0);  // multiple of 16: pitch and x0 are
+        mbar_arrive_expect_tx(&bar[s], rb * (unsigned)rows);
+        const uint8_t *src = img + (size_t)y0 * pitch + x0;
+        for (int r = 0; r < rows; ++r) bulk_copy_g2s(&tile[s][r * MB_ROWB], src + (size_t)r * pitch, rb, &bar[s]);
+    };
+    int it = 0;
+    if (tx == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int tn = t + gridDim.x;
+        if (tx == 0 && tn < n_tiles) issue(tn, s ^ 1);  // stage s^1 was released by the barrier at the end of the previous pass
+        mbar_wait(&bar[s], (unsigned)(it >> 1) & 1u);
+        const int x0 = (t % tiles_x) * MB_COLS, y0 = (t / tiles_x) * MB_ROWS;
+        const int x = x0 + tx;
+        const int y_end = min(y0 + MB_ROWS, height - 8);
+        if (x <= width - 16 && y0 < y_end) {
+            const unsigned sh = (unsigned)(tx & 3) * 8u;
+            moments_strip<true>(reinterpret_cast<const uint32_t *>(&tile[s][tx & ~3]), MB_ROWB >> 2, sh, x, y0, y_end, width, height, mom1,
+                                mom2, mom_pitch, currx);
+        }
+        __syncthreads();  // every thread is done reading stage s before it is refilled two passes later
     }
 }
 
@@ -495,6 +574,30 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
     r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1);
     r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1);
     r.md = __ldg(P.mom2 + o);
+}
+// Optional (DMF_NCC_PREFETCH: 1 = rows + moment table into L1, 2 = into L2, 3 = rows only into L1): prefetch of the NEXT
+// sample's operands while the current sample is computed.  A/B in profiles/r02_ab_ncc_prefetch.txt.
+#ifndef DMF_NCC_PREFETCH
+#define DMF_NCC_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_line(const void *p) {
+#if DMF_NCC_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+template <int WIDTH>
+__device__ __forceinline__ void prefetch_raw(const KParams &P, int ix, int iy) {
+    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
+    const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) prefetch_line(P.currx + o + (size_t)j * W);
+#if DMF_NCC_PREFETCH != 3
+    prefetch_line(P.mom1 + o);
+    prefetch_line(P.mom1 + o + W);
+    prefetch_line(P.mom2 + o);
+#endif
 }
 // cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring
 __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
@@ -626,6 +729,14 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 double fx, fy;
                 split_coord(cx, ix, fx);
                 split_coord(cy, iy, fy);
+#if DMF_NCC_PREFETCH
+                if (j + 1 < L) {
+                    const int nix = __double2loint(__dadd_rd(sx, 4503599627370496.0));
+                    const int niy = __double2loint(__dadd_rd(sy, 4503599627370496.0));
+                    if ((nix != ix || niy != iy) && (unsigned)(nix - 3) < (unsigned)(P.width - 16) && (unsigned)(niy - 3) < (unsigned)(P.height - 12))
+                        prefetch_raw<WIDTH>(P, nix, niy);
+                }
+#endif
                 if (ix != hix || iy != hiy) {
                     RawSample raw;
                     load_raw<WIDTH>(P, ix, iy, raw);

@@ -262,7 +262,10 @@ int dmf_ring_publish(dmf_ring *r, const uint8_t *frame, size_t step, void *wait_
         for (uint32_t c = 0; c < ctl->n_consumers; ++c)
             if (p_wait32((CUstream)r->stream, flag_addr(r, &ctl->released[c][s]), k - S + 1, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
                 return rfail(r, DMF_ERR_CUDA, "dmf_ring_publish: cuStreamWaitValue32 failed");
-    RCU(cudaMemcpy2DAsync(r->slots + (size_t)s * ctl->slot_bytes, ctl->pitch, frame, step, ctl->width, ctl->height, cudaMemcpyDefault, r->stream));
+    if (step == ctl->pitch && ctl->width == ctl->pitch)  // contiguous frame: one linear DMA instead of one descriptor per row
+        RCU(cudaMemcpyAsync(r->slots + (size_t)s * ctl->slot_bytes, frame, ctl->slot_bytes, cudaMemcpyDefault, r->stream));
+    else
+        RCU(cudaMemcpy2DAsync(r->slots + (size_t)s * ctl->slot_bytes, ctl->pitch, frame, step, ctl->width, ctl->height, cudaMemcpyDefault, r->stream));
     if (p_write32((CUstream)r->stream, flag_addr(r, &ctl->filled[s]), k + 1, 0) != CUDA_SUCCESS)
         return rfail(r, DMF_ERR_CUDA, "dmf_ring_publish: cuStreamWriteValue32 failed");
     r->next = k + 1;

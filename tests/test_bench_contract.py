@@ -20,6 +20,9 @@ def test_reference_arm_json_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
     assert j["config"]["workload"] == "remode_640x480"
+    # the reference arm runs none of the product: only the oracle and the input renderer are mapped
+    assert j["native_libs_loaded"] is not None and "libdmf.so" not in j["native_libs_loaded"]
+    assert "liboracle.so" in j["native_libs_loaded"]
 
 
 def test_reference_arm_uses_compiled_reference_when_available():

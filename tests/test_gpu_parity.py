@@ -598,3 +598,31 @@ def test_grouped_divisions_are_bit_identical_to_ieee_division():
     bad = C.c_uint64(123)
     assert _lib.load_dmf().dmf_selftest_division(0, 200_000_000, 20261017, C.byref(bad)) == 0
     assert bad.value == 0
+
+
+def test_moment_table_kernels_agree_bulk_copy_and_legacy(DF, seq640):
+    """moments_bulk_kernel (tiles staged in shared memory by cp.async.bulk + mbarrier) is used when the frame rows are
+    16-byte aligned, moments_kernel otherwise: a device frame with a 4-byte aligned pitch must give the same bits."""
+    import os
+
+    import torch
+    seq, frames = seq640
+    p = seq.params
+    h, w = seq.shape
+    res = []
+    os.environ["DMF_MOMENTS"] = "bulk"  # small frames default to the per-column kernel; read at context creation
+    for pitch in (w, w + 4):  # 640: 16-byte aligned rows (bulk copies); 644: only 4-byte aligned (per-column kernel)
+        dev = torch.zeros((3, h, pitch), dtype=torch.uint8, device="cuda")
+        for i in range(3):
+            dev[i, :, :w] = torch.from_numpy(frames[i + 1]).cuda()
+        torch.cuda.synchronize()
+        f = DF(p)
+        f.set_reference(frames[0])
+        f.fill_state(3.0, 3.0)
+        for i in range(3):
+            f.update_device(dev[i].data_ptr(), pitch, seq.T_C_R(i + 1))
+        res.append(f.download_state() + (f.counters(),))
+        f.close()
+    os.environ.pop("DMF_MOMENTS", None)
+    assert np.array_equal(res[0][0], res[1][0], equal_nan=True) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
+    assert res[0][2] == res[1][2]

@@ -21,7 +21,12 @@ for i in range(n):
     seq.render_device(i, frames[i].data_ptr(), pitch, stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 poses = [seq.T_C_R(i) for i in range(n)]
-for lib in libs:
+for spec in libs:
+    # "path.so" or "path.so:VAR=value[,VAR2=value2]" (environment read by the library at context creation, e.g. DMF_MOMENTS=legacy)
+    lib, _, envs = spec.partition(":")
+    for kv in filter(None, envs.split(",")):
+        k, _, v = kv.partition("=")
+        os.environ[k] = v
     os.environ["DMF_LIB"] = os.path.abspath(lib)
     _lib._cache.pop("dmf", None)
     try:
@@ -48,7 +53,9 @@ for lib in libs:
             f.update_device(frames[i].data_ptr(), pitch, poses[i])
         t = f.timing(reset=True)
         f.close()
-        print(f"{os.path.basename(lib):24s} {wl} n={n}: {best:8.2f} ms  {c['interior']/best/1e6:6.3f} Gpx/s  {c['ncc_evals']/best/1e6:6.2f} GNCC/s | "
+        print(f"{os.path.basename(spec):40s} {wl} n={n}: {best:8.2f} ms  {c['interior']/best/1e6:6.3f} Gpx/s  {c['ncc_evals']/best/1e6:6.2f} GNCC/s | "
               f"setup {t['setup_ms']:.1f} mom {t['moments_ms']:.1f} ncc {t['ncc_ms']:.1f} fuse {t['fuse_ms']:.1f} ms | evals={c['ncc_evals']} sha={dig}", flush=True)
     except Exception as e:  # keep going: one broken variant must not waste the GPU call
-        print(f"{os.path.basename(lib):24s} FAILED: {e!r}", flush=True)
+        print(f"{os.path.basename(spec):24s} FAILED: {e!r}", flush=True)
+    for kv in filter(None, envs.split(",")):
+        os.environ.pop(kv.partition("=")[0], None)
