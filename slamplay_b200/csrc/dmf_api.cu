@@ -58,7 +58,7 @@ struct dmf_ctx_impl {
     // per-frame block-moment table + expanded current frame (moments_kernel), double-buffered by frame parity
     int4 *d_mom1[2] = {nullptr, nullptr};
     dmf::mom2_t *d_mom2[2] = {nullptr, nullptr};
-    uint2 *d_currx[2] = {nullptr, nullptr};
+    dmf::currx_t *d_currx[2] = {nullptr, nullptr};
     cudaEvent_t ev_mom_done[2] = {nullptr, nullptr};  // moments_kernel wrote table b (mom_stream)
     cudaEvent_t ev_tab_free[2] = {nullptr, nullptr};  // ncc_kernel that read table b finished (stream)
     cudaEvent_t ev_adv_done[2] = {nullptr, nullptr};  // advance / setup kernel of update u finished (stream), by parity of u
@@ -437,10 +437,10 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         for (int b = 0; b < 2; ++b) {
             CUX(cudaMalloc(&c->d_mom1[b], W * H * sizeof(int4)));
             CUX(cudaMalloc(&c->d_mom2[b], W * H * sizeof(dmf::mom2_t)));
-            CUX(cudaMalloc(&c->d_currx[b], W * H * sizeof(uint2)));
+            CUX(cudaMalloc(&c->d_currx[b], W * H * sizeof(dmf::currx_t)));
             CUX(cudaMemsetAsync(c->d_mom1[b], 0, W * H * sizeof(int4), c->stream));
             CUX(cudaMemsetAsync(c->d_mom2[b], 0, W * H * sizeof(dmf::mom2_t), c->stream));
-            CUX(cudaMemsetAsync(c->d_currx[b], 0, W * H * sizeof(uint2), c->stream));
+            CUX(cudaMemsetAsync(c->d_currx[b], 0, W * H * sizeof(dmf::currx_t), c->stream));
             CUX(cudaEventCreateWithFlags(&c->ev_mom_done[b], cudaEventDisableTiming));
             CUX(cudaEventCreateWithFlags(&c->ev_tab_free[b], cudaEventDisableTiming));
             CUX(cudaEventCreateWithFlags(&c->ev_adv_done[b], cudaEventDisableTiming));

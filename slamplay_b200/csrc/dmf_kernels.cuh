@@ -101,6 +101,18 @@ struct __align__(16) PixelRec {
 static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 
 typedef int mom2_t;   // the two diagonal Gram terms enter the NCC with the same weight: the table carries their sum
+// Expanded current frame.  Default (DMF_ROWPAIRS = 0): currx[y*W + x] = bytes curr[y][x..x+7] (8 B), a sample fetches the 8
+// rows of its block with eight aligned LDG.64.  DMF_ROWPAIRS = 1 stores {row y, row y+1} (16 B) for FOUR LDG.128 per
+// sample: measured -3 % on ncc_kernel at 1080p (-1 % at 4K) for +30 % on the replicated moments kernel — no gain at 8 GPUs
+// (profiles/r02_ab_rowpairs.txt): the kernel is bound by L1 wavefronts (bytes), not by the number of load instructions.
+#ifndef DMF_ROWPAIRS
+#define DMF_ROWPAIRS 0
+#endif
+#if DMF_ROWPAIRS
+typedef uint4 currx_t;
+#else
+typedef uint2 currx_t;
+#endif
 
 struct KParams {
     int width, height, border;
@@ -122,7 +134,7 @@ struct KParams {
     double ti_norm;       // |t_RC| (ref:525)
     double bd, wd, hd;    // border, width, height as doubles (inside() ref:222-224 without per-sample I2F)
     const uint8_t *curr;  // pitched, 4-byte aligned rows
-    const uint2 *currx;   // expanded current frame: currx[y*width + x] = bytes curr[y][x .. x+7]   (moments_kernel)
+    const currx_t *currx; // expanded current frame (see currx_t; written by moments_kernel)
     const uint8_t *ref;
     const uint2 *refx;    // expanded reference frame: refx[y*width + x] = bytes ref[y][x-3 .. x+3], 0   (ref_expand_kernel)
     const int2 *refstat;  // per pixel: (sum r, 49*sum r^2 - (sum r)^2)
@@ -387,7 +399,7 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
 // sh = 8 * (byte offset of x inside that word).  Rows up to min(y_end + 8, height - 1) are read.
 template <bool SMEM>
 __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsigned sh, int x, int y0, int y_end, int width, int height,
-                                              int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch, uint2 *__restrict__ currx) {
+                                              int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch, currx_t *__restrict__ currx) {
     // window state for position y0: single-row sums over rows y0..y0+6, pair sums over (y0,y0+1)..(y0+6,y0+7)
     int S0 = 0, S1 = 0, Q = 0, H = 0, V = 0, D1 = 0, D2 = 0;
     RowBytes prev = load_row_bytes<SMEM>(wp, sh);
@@ -418,7 +430,11 @@ __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsign
         // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
         // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
         // funnel shifts
+#if DMF_ROWPAIRS
+        currx[(size_t)y * width + x] = make_uint4(old_a.x0l, old_a.hi, old_b.x0l, old_b.hi);  // rows y and y+1
+#else
         currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
+#endif
         // advance the window to position y+1
         S0 = S0n; S1 = S1n;
         Q += rn.q - ro.q; H += rn.h - ro.h;
@@ -432,7 +448,7 @@ __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsign
 
 __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                       int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                      uint2 *__restrict__ currx) {
+                                                      currx_t *__restrict__ currx) {
     const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
     const int y0 = blockIdx.y * MOM_STRIP;
     const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
@@ -476,7 +492,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 __global__ void __launch_bounds__(MB_COLS) moments_bulk_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                                 int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                                uint2 *__restrict__ currx, int tiles_x, int n_tiles) {
+                                                                currx_t *__restrict__ currx, int tiles_x, int n_tiles) {
     __shared__ __align__(16) uint8_t tile[MB_STAGES][MB_TILE_ROWS * MB_ROWB];
     __shared__ __align__(8) uint64_t bar[MB_STAGES];
     const int tx = threadIdx.x;
@@ -564,12 +580,20 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
     const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
     // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
     const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
-    const uint2 *xp = P.currx + o;
+    const currx_t *xp = P.currx + o;
+#if DMF_ROWPAIRS
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const uint4 q = __ldg(xp + (size_t)j * W);
+        r.lo[j] = q.x; r.hi[j] = q.y; r.lo[j + 1] = q.z; r.hi[j + 1] = q.w;
+    }
+#else
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint2 q = __ldg(xp + (size_t)j * W);
         r.lo[j] = q.x; r.hi[j] = q.y;
     }
+#endif
     const int4 *m1 = P.mom1 + o;
     r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1);
     r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1);
