@@ -626,28 +626,55 @@ def e2e_run(args, seq, frames, pitch, torch, device) -> dict:
 
 
 def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, poses, look) -> dict:
-    """N > 1: rank 0 holds the frames in pinned host memory; per update a copy engine moves the frame H2D into the ring on
-    rank 0, every rank pulls it over NVLink with a copy engine and updates its rows; per step gather of the rows and D2H
-    of both maps on rank 0."""
+    """N > 1: the frames live in HOST memory shared by the ranks of the node (POSIX shared memory, page-locked in every
+    rank).  Per update the frame is uploaded by ONE rank (frame k by rank k mod N, so that every GPU's PCIe link carries
+    1/N of the bytes) into that rank's ring slot by a copy engine, every rank pulls it over NVLink with a copy engine and
+    updates its rows; per step gather of the rows and D2H of both maps on rank 0."""
     p = seq.params
     h, w = seq.shape
     F = seq.n_frames
+    shared = args.e2e_host == "shared" and sf.transport == "ring"
+    if shared:  # enough room in /dev/shm for the sequence?  (decided on rank 0, same answer everywhere)
+        ok = [True]
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                ok[0] = st.f_bavail * st.f_frsize > F * h * w + (64 << 20)
+            except OSError:
+                ok[0] = False
+        dist.broadcast_object_list(ok, src=0)
+        shared = bool(ok[0])
     host = None
-    if rank == 0:
+    if shared:
+        arr = sf.shared_host_frames(F)
+        if rank == 0:
+            arr[:] = frames[:, :, :w].cpu().numpy()
+        dist.barrier()
+    elif rank == 0:
         host = torch.empty((F, h, w), dtype=torch.uint8, pin_memory=True)
         host.copy_(frames[:, :, :w])
+    if rank == 0:
         out_d = torch.empty((h, w), dtype=torch.float64, pin_memory=True)
         out_c = torch.empty((h, w), dtype=torch.float64, pin_memory=True)
     torch.cuda.synchronize()
 
     def step():
         sf.fill_state(3.0, 3.0)
-        for j in range(1, min(look, F - 1) + 1):
-            sf.prefetch_host(host[j] if rank == 0 else None)
-        for i in range(1, F):
-            if i + look < F:
-                sf.prefetch_host(host[i + look] if rank == 0 else None)
-            sf.update_host(None, poses[i])
+        if shared:
+            ahead = max(look, world)  # every producer has a frame in flight
+            for j in range(1, min(ahead, F - 1) + 1):
+                sf.prefetch_shared(j)
+            for i in range(1, F):
+                if i + ahead < F:
+                    sf.prefetch_shared(i + ahead)
+                sf.update_shared(poses[i])
+        else:
+            for j in range(1, min(look, F - 1) + 1):
+                sf.prefetch_host(host[j] if rank == 0 else None)
+            for i in range(1, F):
+                if i + look < F:
+                    sf.prefetch_host(host[i + look] if rank == 0 else None)
+                sf.update_host(None, poses[i])
         res = sf.gather_state()
         if rank == 0:
             out_d.copy_(res[0], non_blocking=True)
@@ -666,9 +693,10 @@ def e2e_run_sharded(args, seq, frames, sf, torch, dist, rank, world, device, pos
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     interior = (h - 2 * p.border) * (w - 2 * p.border) * (F - 1)
+    how = (f"frames in shared pinned host memory, frame k uploaded by rank k mod {world} -> copy-engine rings" if shared
+           else f"pinned host frames on rank 0 -> {sf.transport}")
     return {"value": interior / dt, "unit": UNIT, "h2d_bytes_per_step": (F - 1) * h * w, "d2h_bytes_per_step": 16 * h * w,
-            "ms_per_step": dt * 1e3,
-            "api": f"ShardedDepthFilter.update_host (pinned host frames on rank 0 -> {sf.transport}) + gather_state + D2H"}
+            "ms_per_step": dt * 1e3, "api": f"ShardedDepthFilter ({how}) + gather_state + D2H"}
 
 
 def multi_gpu_parity(seq, frames, pitch, gathered, poses_all, torch, device_index, counters_n) -> dict:
@@ -749,6 +777,8 @@ def main():
     ap.add_argument("--block-rows", type=int, default=8, help="rows per block of the cyclic layout")
     ap.add_argument("--ring", type=int, default=4, help="slots of the frame ring for N > 1 (>= 2)")
     ap.add_argument("--transport", default="auto", choices=["auto", "ring", "broadcast"], help="frame distribution for N > 1")
+    ap.add_argument("--e2e-host", default="shared", choices=["shared", "rank0"],
+                    help="N > 1 end-to-end run: host frames in shared memory uploaded by all ranks in turn, or held and uploaded by rank 0")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the nested 1920x1080 and strict drop-in blocks")

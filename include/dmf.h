@@ -217,9 +217,13 @@ int dmf_stream(dmf_ctx *ctx, void **stream);
  */
 int dmf_selftest_division(int device, uint64_t n, uint64_t seed, uint64_t *mismatches);
 
-/* Pinned host memory helpers for zero-staging dmf_update() calls. */
+/* Pinned host memory helpers for zero-staging dmf_update() calls.  dmf_host_register page-locks memory the caller
+ * already owns (e.g. a POSIX shared-memory mapping of the frames that several ranks publish from, one frame each in
+ * turn, so that the uploads use every GPU's PCIe link). */
 int dmf_alloc_pinned(void **ptr, size_t bytes);
 int dmf_free_pinned(void *ptr);
+int dmf_host_register(void *ptr, size_t bytes);
+int dmf_host_unregister(void *ptr);
 
 /*
  * "Next" rows — consumers of the maps, evaluated on the device so a

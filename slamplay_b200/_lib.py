@@ -100,6 +100,8 @@ DMF_SYMBOLS = {
     "dmf_selftest_division": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _P(C.c_uint64)]),
     "dmf_alloc_pinned": (C.c_int, [_P(_vp), C.c_size_t]),
     "dmf_free_pinned": (C.c_int, [_vp]),
+    "dmf_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "dmf_host_unregister": (C.c_int, [_vp]),
     "dmf_set_truth": (C.c_int, [_vp, _vp, C.c_size_t]),
     "dmf_evaluate_depth": (C.c_int, [_vp, C.c_double, _P(C.c_double), _P(C.c_uint64)]),
     "dmf_variance_mask": (C.c_int, [_vp, C.c_double, _vp, C.c_size_t]),

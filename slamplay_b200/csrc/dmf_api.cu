@@ -73,6 +73,8 @@ struct dmf_ctx_impl {
     bool timing_on = false;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    std::vector<cudaEvent_t> ev_flush;         // pairs around the stand-alone fuse_kernel launched by flush_pending (timing on)
+    size_t ev_flush_used = 0;
     double timing_ms[4] = {0, 0, 0, 0};
     unsigned long long timing_frames = 0;
     bool have_ref = false, flags_on = false, have_truth = false;
@@ -172,7 +174,19 @@ int flush_pending(dmf_ctx_impl *c) {
     dmf::KParams K{};
     fill_kparams(c, K, c->seq - 1);
     fill_finish(c, K, c->seq - 1);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing_on) {  // the deferred fusion of the last update of a sequence belongs to the per-kernel split as well
+        while (c->ev_flush.size() < c->ev_flush_used + 2) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->ev_flush.push_back(e);
+        }
+        e0 = c->ev_flush[c->ev_flush_used++];
+        e1 = c->ev_flush[c->ev_flush_used++];
+        CU(cudaEventRecord(e0, c->stream));
+    }
     dmf::fuse_kernel<<<dim3(c->tiles_x, c->n_bands), dmf::TILE_PIX, 0, c->stream>>>(K);
+    if (e1) CU(cudaEventRecord(e1, c->stream));
     CU(cudaGetLastError());
     c->pending = false;
     return DMF_OK;
@@ -525,6 +539,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
     for (int b = 0; b < 2; ++b) if (ctx->h_shadow[b]) cudaFreeHost(ctx->h_shadow[b]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_flush) cudaEventDestroy(e);
     cudaFree(ctx->d_refstat); cudaFree(ctx->d_depth); cudaFree(ctx->d_cov2); cudaFree(ctx->d_truth);
     cudaFree(ctx->d_dbg_ncc); cudaFree(ctx->d_dbg_n);
     for (int b = 0; b < 2; ++b) { cudaFree(ctx->d_rec[b]); cudaFree(ctx->d_best[b]); cudaFree(ctx->d_state_c[b]); }
@@ -803,6 +818,12 @@ int dmf_get_timing(dmf_ctx *c, double ms_out[4], uint64_t *frames, int reset) {
         c->timing_frames++;
     }
     c->ev_used = 0;
+    for (size_t i = 0; i + 1 < c->ev_flush_used; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev_flush[i], c->ev_flush[i + 1]));
+        c->timing_ms[3] += ms;
+    }
+    c->ev_flush_used = 0;
     for (int k = 0; k < 4; ++k) ms_out[k] = c->timing_ms[k];
     *frames = c->timing_frames;
     if (reset) { for (int k = 0; k < 4; ++k) c->timing_ms[k] = 0; c->timing_frames = 0; }
@@ -881,6 +902,19 @@ int dmf_alloc_pinned(void **ptr, size_t bytes) {
     dmf_ctx_impl *c = nullptr;
     if (!ptr) return fail(c, DMF_ERR_INVALID, "dmf_alloc_pinned: NULL argument");
     CU(cudaMallocHost(ptr, bytes));
+    return DMF_OK;
+}
+
+int dmf_host_register(void *ptr, size_t bytes) {
+    dmf_ctx_impl *c = nullptr;
+    if (!ptr || !bytes) return fail(c, DMF_ERR_INVALID, "dmf_host_register: NULL argument");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return DMF_OK;
+}
+
+int dmf_host_unregister(void *ptr) {
+    dmf_ctx_impl *c = nullptr;
+    if (ptr) CU(cudaHostUnregister(ptr));
     return DMF_OK;
 }
 

@@ -64,3 +64,43 @@ class FrameRing:
             self.close()
         except Exception:
             pass
+
+
+class SharedHostFrames:
+    """A stack of frames (F, H, W) uint8 in POSIX shared memory, mapped and page-locked (dmf_host_register) by every rank
+    of the node.  With the frames visible to all ranks, each rank can publish "its" frames (frame k by rank k mod N) into
+    its own ring, so that the host-to-device uploads are spread over all PCIe links instead of rank 0's alone."""
+
+    def __init__(self, name: str, shape, create: bool):
+        import numpy as np
+        self._lib = _lib.load_dmf()
+        self.name, self.shape, self.created = name, tuple(int(v) for v in shape), create
+        path = "/dev/shm/" + name
+        self.array = np.memmap(path, dtype=np.uint8, mode="w+" if create else "r+", shape=self.shape)
+        self.nbytes = int(np.prod(self.shape))
+        self._ptr = self.array.ctypes.data
+        rc = self._lib.dmf_host_register(C.c_void_p(self._ptr), self.nbytes)
+        if rc != 0:
+            raise RingError(f"dmf_host_register failed ({rc}): {self._lib.dmf_last_error(None).decode()}")
+        self._registered = True
+
+    def frame_ptr(self, i: int) -> int:
+        return self._ptr + i * self.shape[1] * self.shape[2]
+
+    def close(self) -> None:
+        if getattr(self, "_registered", False):
+            self._lib.dmf_host_unregister(C.c_void_p(self._ptr))
+            self._registered = False
+            del self.array
+            if self.created:
+                import os
+                try:
+                    os.unlink("/dev/shm/" + self.name)
+                except OSError:
+                    pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

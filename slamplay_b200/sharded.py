@@ -93,7 +93,10 @@ class ShardedDepthFilter:
         self.n_ring = n_ring
         self.transport = transport
         self.frame_ring = self.frame_ring_out = None
+        self.frame_rings = []          # ring p (producer = rank p) opened as consumer `rank`; ring 0 = frame_ring
+        self.shared_frames = None
         self._published = self._consumed = 0
+        self._shared_pub = self._shared_con = 0
         self._attach(device, n_ring)
         if self.transport == "auto":
             self.transport = "ring" if (self.world > 1 and getattr(self.tdev, "type", "cpu") == "cuda" and self.filter is not None) else "broadcast"
@@ -123,18 +126,59 @@ class ShardedDepthFilter:
         self.cov2_t = torch.as_tensor(_DevArray(c_ptr, (self.H, self.W), "<f8"), device=dev)
 
     def _attach_ring(self) -> None:
-        """Rank 0 creates the frame ring, every rank (rank 0 included) opens it as consumer number `rank`."""
+        """Every rank creates a frame ring in its own HBM and opens all of them as consumer number `rank`.  Ring 0 (rank 0)
+        carries the frames that rank 0 alone holds (device-resident sequences, host frames private to rank 0); with host
+        frames in shared memory (shared_host_frames) frame k is published by rank k mod N into ring k mod N, so that the
+        uploads use every GPU's PCIe link."""
         from .frame_ring import FrameRing
         dist = self.dist
-        box = [None]
-        if self.rank == 0:
-            self.frame_ring_out = FrameRing.create(self.device, self.n_ring, self.W, self.H, self.world)
-            box[0] = self.frame_ring_out.handle
+        self.frame_ring_out = FrameRing.create(self.device, self.n_ring, self.W, self.H, self.world)
+        handles = [None] * self.world
         if self.world > 1:
-            dist.broadcast_object_list(box, src=0, group=self.group)
-        self.frame_ring = FrameRing.open(self.device, box[0], self.rank)
+            dist.all_gather_object(handles, self.frame_ring_out.handle, group=self.group)
+        else:
+            handles[0] = self.frame_ring_out.handle
+        self.frame_rings = [FrameRing.open(self.device, h, self.rank) for h in handles]
+        self.frame_ring = self.frame_rings[0]
         if self.world > 1:
             dist.barrier(group=self.group)
+
+    # -- host frames shared by all ranks of the node -------------------------------------------------------
+    def shared_host_frames(self, n_frames: int):
+        """Collective.  A (n_frames, H, W) uint8 numpy array in POSIX shared memory, page-locked in every rank; rank 0
+        fills it (then call a barrier).  prefetch_shared(i) / update_shared(pose) then publish frame i from rank
+        i mod N: every rank uploads 1/N of the frames over its own PCIe link."""
+        import os
+
+        from .frame_ring import SharedHostFrames
+        if self.transport != "ring":
+            raise RuntimeError("shared host frames need the ring transport")
+        box = [f"dmf_frames_{os.getpid()}_{id(self) & 0xffffff:x}" if self.rank == 0 else None]
+        if self.rank == 0:
+            self.shared_frames = SharedHostFrames(box[0], (n_frames, self.H, self.W), create=True)
+        if self.world > 1:
+            self.dist.broadcast_object_list(box, src=0, group=self.group)
+            if self.rank != 0:
+                self.shared_frames = SharedHostFrames(box[0], (n_frames, self.H, self.W), create=False)
+            self.dist.barrier(group=self.group)
+        self._shared_pub = self._shared_con = 0
+        return self.shared_frames.array
+
+    def prefetch_shared(self, i: int) -> None:
+        """Announce frame i of the shared host frames (call in the same order on every rank): its producer, rank
+        (n-th announced frame) mod N, enqueues the H2D copy into its ring."""
+        k = self._shared_pub
+        self._shared_pub += 1
+        if k - self._shared_con >= self.n_ring * self.world:
+            raise RuntimeError("more frames announced than ring slots: call update_shared() before announcing more")
+        if k % self.world == self.rank:
+            self.frame_ring_out.publish(self.shared_frames.frame_ptr(i), self.W, None)
+
+    def update_shared(self, pose) -> None:
+        """update() against the next announced frame of the shared host frames."""
+        k = self._shared_con
+        self._shared_con += 1
+        self.filter.update_ring(self.frame_rings[k % self.world], pose)
 
     def _ring_publish(self, frame_dev, host_frame) -> None:
         if self.rank != 0:
@@ -334,9 +378,12 @@ class ShardedDepthFilter:
             self.filter.sync()
         if self.world > 1 and self.frame_ring is not None:
             self.dist.barrier(group=self.group)  # nobody unmaps the ring while a peer is still pulling from it
-        for r in (self.frame_ring, self.frame_ring_out):
+        for r in list(self.frame_rings) + [self.frame_ring_out]:
             if r is not None:
                 r.close()
-        self.frame_ring = self.frame_ring_out = None
+        self.frame_rings, self.frame_ring, self.frame_ring_out = [], None, None
+        if self.shared_frames is not None:
+            self.shared_frames.close()
+            self.shared_frames = None
         if self.filter is not None:
             self.filter.close()
