@@ -599,6 +599,31 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
     r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1);
     r.md = __ldg(P.mom2 + o);
 }
+// DMF_NCC_CARRY: consecutive samples of a search are 0.7 px apart, so a new integer position is usually a neighbour of
+// the previous one, and two of its four moment-table entries are already in registers (entry (x+1,y) of the old
+// position is entry (x,y) of the position one step to the right, ...).  Only the two missing entries are loaded:
+// 9 L1 wavefronts instead of 17 for the moment table of an axis-aligned step (the kernel is bound by L1 wavefronts).
+#ifndef DMF_NCC_CARRY
+#define DMF_NCC_CARRY 0
+#endif
+template <int WIDTH>
+__device__ __forceinline__ void load_raw_carry(const KParams &P, int ix, int iy, int dx, int dy, RawSample &r) {
+    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
+    const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
+    const currx_t *xp = P.currx + o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(xp + (size_t)j * W));
+        r.lo[j] = q.x; r.hi[j] = q.y;
+    }
+    const int4 *m1 = P.mom1 + o;
+    if (dy == 0 && dx == 1) { r.m00 = r.m10; r.m01 = r.m11; r.m10 = __ldg(m1 + 1); r.m11 = __ldg(m1 + W + 1); }
+    else if (dy == 0 && dx == -1) { r.m10 = r.m00; r.m11 = r.m01; r.m00 = __ldg(m1); r.m01 = __ldg(m1 + W); }
+    else if (dx == 0 && dy == 1) { r.m00 = r.m01; r.m10 = r.m11; r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1); }
+    else if (dx == 0 && dy == -1) { r.m01 = r.m00; r.m11 = r.m10; r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1); }
+    else { r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1); r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1); }
+    r.md = __ldg(P.mom2 + o);
+}
 // Optional (DMF_NCC_PREFETCH: 1 = rows + moment table into L1, 2 = into L2, 3 = rows only into L1): prefetch of the NEXT
 // sample's operands while the current sample is computed.  A/B in profiles/r02_ab_ncc_prefetch.txt.
 #ifndef DMF_NCC_PREFETCH
@@ -734,6 +759,10 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
             int best_k = -1;
             int hix = -1, hiy = -1;  // integer position whose SampleInts are held
             SampleInts si{};
+#if DMF_NCC_CARRY
+            RawSample raw;           // its moment-table entries are carried from one position to the next
+            raw.m00 = raw.m10 = raw.m01 = raw.m11 = make_int4(0, 0, 0, 0);
+#endif
             // l of the unit's first sample: k0 additions of the step, as the reference accumulates them (ref:432);
             // inside the loop the position of sample j+1 is computed before the NCC of sample j (off the critical path)
             double sx, sy;
@@ -762,8 +791,12 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 }
 #endif
                 if (ix != hix || iy != hiy) {
+#if DMF_NCC_CARRY
+                    load_raw_carry<WIDTH>(P, ix, iy, ix - hix, iy - hiy, raw);
+#else
                     RawSample raw;
                     load_raw<WIDTH>(P, ix, iy, raw);
+#endif
                     si = reduce_raw(raw, R0lo, R0hi, R1lo, R1hi, nSr);
                     hix = ix; hiy = iy;
                 }
