@@ -80,3 +80,27 @@ def test_product_package_never_references_the_oracle():
             txt = f.read_text()
             assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
             assert "liboracle" not in txt and "dmo_" not in txt, f"{f} links against the oracle"
+
+
+def test_ring_and_strict_entry_points_validate_arguments_without_a_gpu():
+    """The multi-GPU frame ring and the strict drop-in reject bad arguments before touching CUDA; with valid arguments
+    and no device they fail loudly (no CPU fallback)."""
+    lib = _lib.load_dmf()
+    ring = C.c_void_p()
+    handle = (C.c_uint8 * 192)()
+    assert lib.dmf_ring_create(0, 1, 640, 480, 2, C.byref(ring), handle) == -1      # n_slots < 2
+    assert lib.dmf_ring_create(0, 4, 640, 480, 0, C.byref(ring), handle) == -1      # no consumers
+    assert lib.dmf_ring_create(0, 4, 640, 480, 2, None, handle) == -1
+    assert lib.dmf_ring_open(0, handle, 0, C.byref(ring)) == -1                     # zeroed bytes are not a ring handle
+    assert b"not a ring handle" in lib.dmf_last_error(None)
+    assert lib.dmf_update_ring(None, None, None, None) == -1
+    assert lib.dmf_ring_publish(None, None, 0, None) == -1
+    assert lib.dmf_update_strict(None, None, 0, None, 0, None, None, None, 0, None, 0) == -1
+    assert lib.dmf_host_register(None, 0) == -1
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.dmf_ring_create(0, 4, 640, 480, 2, C.byref(ring), handle) == -2  # DMF_ERR_CUDA: no device, no fallback
+        peaks = _lib.DmfPipePeaks()
+        assert lib.dmf_pipe_peaks(0, C.byref(peaks)) == -2
+        bad = C.c_uint64()
+        assert lib.dmf_selftest_division(0, 10, 1, C.byref(bad)) == -2

@@ -201,3 +201,65 @@ def test_cuda_branch_of_the_frame_pipeline_with_mock_streams(monkeypatch):
     # without look-ahead the same calls fall back to transfer-then-launch
     sf.update_host(host[3], ("q", 99))
     assert sf.launched[-1][:2] == (3, ("q", 99)) and not sf._queue
+
+
+def test_shared_host_frames_round_robin_bookkeeping():
+    """Multi-producer rings (frame k uploaded by rank k mod N into ring k mod N, consumed by every rank from that ring in
+    order): the bookkeeping of prefetch_shared / update_shared, with recording stand-ins for the rings and the filter."""
+    import types
+
+    from slamplay_b200.sharded import ShardedDepthFilter
+    from slamplay_b200.synth import make_sequence
+
+    seq = make_sequence("tiny", width=192, height=128, n_frames=4)
+    world, n_ring, F = 3, 2, 14
+    log = {"pub": [], "con": []}
+
+    class FakeRing:
+        def __init__(self, owner):
+            self.owner = owner
+
+        def publish(self, ptr, step, stream):
+            log["pub"].append((self.owner, ptr))
+
+    class FakeFilter:
+        def __init__(self, rank):
+            self.rank = rank
+
+        def update_ring(self, ring, pose):
+            log["con"].append((self.rank, ring.owner, pose))
+
+    class Mock(ShardedDepthFilter):
+        def _attach(self, device, n_ring):
+            self.tdev = types.SimpleNamespace(type="cpu")
+            self.filter = None
+
+    ranks = []
+    for r in range(world):
+        sf = Mock(seq.params, n_ring=n_ring, transport="broadcast")
+        sf.rank, sf.world, sf.transport = r, world, "ring"
+        sf.filter = FakeFilter(r)
+        sf.frame_ring_out = FakeRing(r)
+        sf.frame_rings = [FakeRing(p) for p in range(world)]
+        sf.shared_frames = types.SimpleNamespace(frame_ptr=lambda i: 1000 + i)
+        ranks.append(sf)
+    ahead = world
+    for sf in ranks:  # every rank runs the same loop (bench.py e2e_run_sharded)
+        for j in range(1, ahead + 1):
+            sf.prefetch_shared(j)
+        for i in range(1, F):
+            if i + ahead < F:
+                sf.prefetch_shared(i + ahead)
+            sf.update_shared(("pose", i))
+    # frame i (the (i-1)-th announced) is published exactly once, by rank (i-1) mod N, from the shared buffer
+    assert sorted(log["pub"]) == sorted(((i - 1) % world, 1000 + i) for i in range(1, F))
+    # every rank consumes update i from the ring of that producer, in order
+    for r in range(world):
+        mine = [(owner, pose[1]) for (rk, owner, pose) in log["con"] if rk == r]
+        assert mine == [((i - 1) % world, i) for i in range(1, F)]
+    # the look-ahead is bounded by the ring capacity
+    import pytest
+    sf = ranks[0]
+    with pytest.raises(RuntimeError):
+        for i in range(n_ring * world + 1):
+            sf.prefetch_shared(i)
