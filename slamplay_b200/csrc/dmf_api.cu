@@ -465,12 +465,16 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_cta_cnt, 2 * (size_t)c->n_ctas * sizeof(unsigned int)));
         CUX(cudaMemsetAsync(c->d_cta_cnt, 0, 2 * (size_t)c->n_ctas * sizeof(unsigned int), c->stream));
         int per_sm = 0;
+        // 4 CTAs / SM with the block shifted per sample (80 registers) where the per-frame tables exceed L2 (>= 4 M pixels:
+        // measured -5 % on ncc_kernel at 4K), 3 CTAs / SM with the pre-shifted patch copy otherwise (DMF_NCC_SB=0/1 forces)
+        const char *sbe = std::getenv("DMF_NCC_SB");
+        const bool sb = sbe ? std::atoi(sbe) != 0 : (size_t)params->width * params->height >= (4u << 20);
         switch (params->width) {  // compile-time widths: the row loads of a sample become immediate offsets
-            case 640: c->ncc_fn = dmf::ncc_kernel<640>; break;
-            case 1241: c->ncc_fn = dmf::ncc_kernel<1241>; break;
-            case 1920: c->ncc_fn = dmf::ncc_kernel<1920>; break;
-            case 3840: c->ncc_fn = dmf::ncc_kernel<3840>; break;
-            default: c->ncc_fn = dmf::ncc_kernel<0>; break;
+            case 640: c->ncc_fn = sb ? dmf::ncc_kernel<640, true> : dmf::ncc_kernel<640, false>; break;
+            case 1241: c->ncc_fn = sb ? dmf::ncc_kernel<1241, true> : dmf::ncc_kernel<1241, false>; break;
+            case 1920: c->ncc_fn = sb ? dmf::ncc_kernel<1920, true> : dmf::ncc_kernel<1920, false>; break;
+            case 3840: c->ncc_fn = sb ? dmf::ncc_kernel<3840, true> : dmf::ncc_kernel<3840, false>; break;
+            default: c->ncc_fn = sb ? dmf::ncc_kernel<0, true> : dmf::ncc_kernel<0, false>; break;
         }
         {
             // Kernels that are to share an SM must agree on its L1 / shared-memory split: ncc_kernel uses no shared memory,

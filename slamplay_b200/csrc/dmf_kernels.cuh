@@ -648,12 +648,30 @@ __device__ __forceinline__ void prefetch_raw(const KParams &P, int ix, int iy) {
     prefetch_line(P.mom2 + o);
 #endif
 }
-// cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring
+// cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring.
+// SHIFT_BLOCK: the windows a = 1 (block columns 1..7) are formed by shifting the BLOCK row by one byte per sample
+// (2 ALU ops per row) instead of holding a second, byte-shifted copy of the reference patch (14 registers less: 80
+// instead of 96, i.e. 4 instead of 3 CTAs per SM).
+// Selected per context: 4 CTAs per SM (80 registers, 24 warps) pay off where the tables exceed L2 (4K: -5 % on ncc_kernel),
+// not at 1080p and below (profiles/r02_ab_ncc_shift_block.txt).
+template <bool SHIFT_BLOCK>
 __device__ __forceinline__ SampleInts reduce_raw(const RawSample &r, const uint32_t (&R0lo)[7], const uint32_t (&R0hi)[7],
                                                  const uint32_t (&R1lo)[7], const uint32_t (&R1hi)[7], int nSr) {
     int R00 = 0, R10 = 0, R01 = 0, R11 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+        if (SHIFT_BLOCK) {
+            const uint32_t lo1 = __funnelshift_r(r.lo[j], r.hi[j], 8), hi1 = r.hi[j] >> 8;
+            if (j > 0) {
+                R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
+                R11 = dp4(R0lo[j - 1], lo1, dp4(R0hi[j - 1], hi1, R11));
+            }
+            if (j < 7) {
+                R00 = dp4(R0lo[j], r.lo[j], dp4(R0hi[j], r.hi[j], R00));
+                R10 = dp4(R0lo[j], lo1, dp4(R0hi[j], hi1, R10));
+            }
+            continue;
+        }
         if (j > 0) {
             R01 = dp4(R0lo[j - 1], r.lo[j], dp4(R0hi[j - 1], r.hi[j], R01));
             R11 = dp4(R1lo[j - 1], r.lo[j], dp4(R1hi[j - 1], r.hi[j], R11));
@@ -703,8 +721,8 @@ __device__ __forceinline__ void fetch_units(const KParams &P, const unsigned (&c
     }
 }
 
-template <int WIDTH>
-__global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
+template <int WIDTH, bool SHIFT_BLOCK>
+__global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS + 1 : DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
     const int lane = threadIdx.x & 31;
     // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
     unsigned counts[CHUNK + 1];
@@ -751,7 +769,8 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                 for (int j = 0; j < 7; ++j) {
                     const uint2 q = __ldg(rp + (size_t)j * W);
                     R0lo[j] = q.x; R0hi[j] = q.y;
-                    R1lo[j] = q.x << 8; R1hi[j] = __funnelshift_l(q.x, q.y, 8);
+                    if (SHIFT_BLOCK) { R1lo[j] = 0; R1hi[j] = 0; }  // unused: the block is shifted instead (reduce_raw)
+                    else { R1lo[j] = q.x << 8; R1hi[j] = __funnelshift_l(q.x, q.y, 8); }
                 }
             }
 
@@ -797,7 +816,7 @@ __global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS) ncc_kernel(co
                     RawSample raw;
                     load_raw<WIDTH>(P, ix, iy, raw);
 #endif
-                    si = reduce_raw(raw, R0lo, R0hi, R1lo, R1hi, nSr);
+                    si = reduce_raw<SHIFT_BLOCK>(raw, R0lo, R0hi, R1lo, R1hi, nSr);
                     hix = ix; hiy = iy;
                 }
                 const double v = ncc_combine(si, den1, fx, fy);
