@@ -101,18 +101,10 @@ struct __align__(16) PixelRec {
 static_assert(sizeof(PixelRec) == 64, "PixelRec must be 64 bytes");
 
 typedef int mom2_t;   // the two diagonal Gram terms enter the NCC with the same weight: the table carries their sum
-// Expanded current frame.  Default (DMF_ROWPAIRS = 0): currx[y*W + x] = bytes curr[y][x..x+7] (8 B), a sample fetches the 8
-// rows of its block with eight aligned LDG.64.  DMF_ROWPAIRS = 1 stores {row y, row y+1} (16 B) for FOUR LDG.128 per
-// sample: measured -3 % on ncc_kernel at 1080p (-1 % at 4K) for +30 % on the replicated moments kernel — no gain at 8 GPUs
-// (profiles/r02_ab_rowpairs.txt): the kernel is bound by L1 wavefronts (bytes), not by the number of load instructions.
-#ifndef DMF_ROWPAIRS
-#define DMF_ROWPAIRS 0
-#endif
-#if DMF_ROWPAIRS
-typedef uint4 currx_t;
-#else
+// Expanded current frame: currx[y*W + x] = bytes curr[y][x..x+7] as one aligned 64-bit word (a sample fetches each row of
+// its 8x8 block with one LDG.64).  Storing row PAIRS (16 B, four LDG.128 per sample) was measured: -3 % on ncc_kernel at
+// 1080p, +30 % on the replicated moments kernel, no gain at 8 GPUs (profiles/r02_ab_rowpairs.txt, commit f0b8015).
 typedef uint2 currx_t;
-#endif
 
 struct KParams {
     int width, height, border;
@@ -345,13 +337,6 @@ __global__ void __launch_bounds__(TILE_PIX) setup_kernel(const __grid_constant__
 }
 
 // ----------------------------------------------------------------------------------------
-// Loads 8 bytes starting at an arbitrary byte address from 4-byte aligned words.
-__device__ __forceinline__ void load_row8(const uint32_t *wp, unsigned sh, uint32_t &lo, uint32_t &hi) {
-    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-    lo = __funnelshift_r(w0, w1, sh);
-    hi = __funnelshift_r(w1, w2, sh);
-}
-
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
 
 // K2m: once per current frame — the frame-only part of every possible NCC: window sum and centred
@@ -430,11 +415,7 @@ __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsign
         // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
         // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
         // funnel shifts
-#if DMF_ROWPAIRS
-        currx[(size_t)y * width + x] = make_uint4(old_a.x0l, old_a.hi, old_b.x0l, old_b.hi);  // rows y and y+1
-#else
         currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
-#endif
         // advance the window to position y+1
         S0 = S0n; S1 = S1n;
         Q += rn.q - ro.q; H += rn.h - ro.h;
@@ -581,73 +562,20 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
     // one element offset for the three tables (their pitch is the image width; W*H < 2^31)
     const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
     const currx_t *xp = P.currx + o;
-#if DMF_ROWPAIRS
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        const uint4 q = __ldg(xp + (size_t)j * W);
-        r.lo[j] = q.x; r.hi[j] = q.y; r.lo[j + 1] = q.z; r.hi[j + 1] = q.w;
-    }
-#else
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint2 q = __ldg(xp + (size_t)j * W);
         r.lo[j] = q.x; r.hi[j] = q.y;
     }
-#endif
     const int4 *m1 = P.mom1 + o;
     r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1);
     r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1);
     r.md = __ldg(P.mom2 + o);
 }
-// DMF_NCC_CARRY: consecutive samples of a search are 0.7 px apart, so a new integer position is usually a neighbour of
-// the previous one, and two of its four moment-table entries are already in registers (entry (x+1,y) of the old
-// position is entry (x,y) of the position one step to the right, ...).  Only the two missing entries are loaded:
-// 9 L1 wavefronts instead of 17 for the moment table of an axis-aligned step (the kernel is bound by L1 wavefronts).
-#ifndef DMF_NCC_CARRY
-#define DMF_NCC_CARRY 0
-#endif
-template <int WIDTH>
-__device__ __forceinline__ void load_raw_carry(const KParams &P, int ix, int iy, int dx, int dy, RawSample &r) {
-    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
-    const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
-    const currx_t *xp = P.currx + o;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(xp + (size_t)j * W));
-        r.lo[j] = q.x; r.hi[j] = q.y;
-    }
-    const int4 *m1 = P.mom1 + o;
-    if (dy == 0 && dx == 1) { r.m00 = r.m10; r.m01 = r.m11; r.m10 = __ldg(m1 + 1); r.m11 = __ldg(m1 + W + 1); }
-    else if (dy == 0 && dx == -1) { r.m10 = r.m00; r.m11 = r.m01; r.m00 = __ldg(m1); r.m01 = __ldg(m1 + W); }
-    else if (dx == 0 && dy == 1) { r.m00 = r.m01; r.m10 = r.m11; r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1); }
-    else if (dx == 0 && dy == -1) { r.m01 = r.m00; r.m11 = r.m10; r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1); }
-    else { r.m00 = __ldg(m1); r.m10 = __ldg(m1 + 1); r.m01 = __ldg(m1 + W); r.m11 = __ldg(m1 + W + 1); }
-    r.md = __ldg(P.mom2 + o);
-}
-// Optional (DMF_NCC_PREFETCH: 1 = rows + moment table into L1, 2 = into L2, 3 = rows only into L1): prefetch of the NEXT
-// sample's operands while the current sample is computed.  A/B in profiles/r02_ab_ncc_prefetch.txt.
-#ifndef DMF_NCC_PREFETCH
-#define DMF_NCC_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetch_line(const void *p) {
-#if DMF_NCC_PREFETCH == 2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-template <int WIDTH>
-__device__ __forceinline__ void prefetch_raw(const KParams &P, int ix, int iy) {
-    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
-    const unsigned o = (unsigned)(iy - 3) * W + (unsigned)(ix - 3);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) prefetch_line(P.currx + o + (size_t)j * W);
-#if DMF_NCC_PREFETCH != 3
-    prefetch_line(P.mom1 + o);
-    prefetch_line(P.mom1 + o + W);
-    prefetch_line(P.mom2 + o);
-#endif
-}
+// Measured and dropped (bit-identical results, slower): prefetching the next sample's lines (CCTL.PF1, +34 %:
+// profiles/r02_ab_ncc_prefetch_and_moments.txt, commit 04641b5) and carrying moment-table entries between neighbouring
+// integer positions in registers (the per-lane step-type branches serialise the loads, +28 %: profiles/r02_ab_ncc_carry.txt,
+// commit 43954c3).  The kernel is bound by L1 wavefronts (bytes) and by the latency of L1 misses, not by load instructions.
 // cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring.
 // SHIFT_BLOCK: the windows a = 1 (block columns 1..7) are formed by shifting the BLOCK row by one byte per sample
 // (2 ALU ops per row) instead of holding a second, byte-shifted copy of the reference patch (14 registers less: 80
@@ -778,10 +706,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
             int best_k = -1;
             int hix = -1, hiy = -1;  // integer position whose SampleInts are held
             SampleInts si{};
-#if DMF_NCC_CARRY
-            RawSample raw;           // its moment-table entries are carried from one position to the next
-            raw.m00 = raw.m10 = raw.m01 = raw.m11 = make_int4(0, 0, 0, 0);
-#endif
             // l of the unit's first sample: k0 additions of the step, as the reference accumulates them (ref:432);
             // inside the loop the position of sample j+1 is computed before the NCC of sample j (off the critical path)
             double sx, sy;
@@ -801,21 +725,9 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
                 double fx, fy;
                 split_coord(cx, ix, fx);
                 split_coord(cy, iy, fy);
-#if DMF_NCC_PREFETCH
-                if (j + 1 < L) {
-                    const int nix = __double2loint(__dadd_rd(sx, 4503599627370496.0));
-                    const int niy = __double2loint(__dadd_rd(sy, 4503599627370496.0));
-                    if ((nix != ix || niy != iy) && (unsigned)(nix - 3) < (unsigned)(P.width - 16) && (unsigned)(niy - 3) < (unsigned)(P.height - 12))
-                        prefetch_raw<WIDTH>(P, nix, niy);
-                }
-#endif
                 if (ix != hix || iy != hiy) {
-#if DMF_NCC_CARRY
-                    load_raw_carry<WIDTH>(P, ix, iy, ix - hix, iy - hiy, raw);
-#else
                     RawSample raw;
                     load_raw<WIDTH>(P, ix, iy, raw);
-#endif
                     si = reduce_raw<SHIFT_BLOCK>(raw, R0lo, R0hi, R1lo, R1hi, nSr);
                     hix = ix; hiy = iy;
                 }
