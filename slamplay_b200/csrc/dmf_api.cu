@@ -59,9 +59,6 @@ struct dmf_ctx_impl {
     int4 *d_mom1[2] = {nullptr, nullptr};
     dmf::mom2_t *d_mom2[2] = {nullptr, nullptr};
     dmf::currx_t *d_currx[2] = {nullptr, nullptr};
-    void *d_tab[2] = {nullptr, nullptr};       // one allocation per table buffer: mom1 | currx | mom2 (one L2 access-policy window covers it)
-    size_t tab_bytes = 0;
-    float l2_hit_ratio = 0.f;                  // > 0: the table buffer of the running update is requested to persist in L2
     cudaEvent_t ev_mom_done[2] = {nullptr, nullptr};  // moments_kernel wrote table b (mom_stream)
     cudaEvent_t ev_tab_free[2] = {nullptr, nullptr};  // ncc_kernel that read table b finished (stream)
     cudaEvent_t ev_adv_done[2] = {nullptr, nullptr};  // advance / setup kernel of update u finished (stream), by parity of u
@@ -236,16 +233,6 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             // register file) the precompute would only take its place in the queue; beside ncc_kernel it runs in the
             // registers that kernel leaves free
             if (c->mom_gate && u > 0) CU(cudaStreamWaitEvent(ms, c->ev_adv_done[b ^ 1], 0));
-        }
-        if (c->l2_hit_ratio > 0.f) {
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = c->d_tab[b];
-            av.accessPolicyWindow.num_bytes = c->tab_bytes;
-            av.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            CU(cudaStreamSetAttribute(ms, cudaStreamAttributeAccessPolicyWindow, &av));           // the writer (moments)
-            if (ms != c->stream) CU(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));  // the reader (ncc)
         }
         if (ev[0]) CU(cudaEventRecord(ev[0], c->stream));
         if (merged) dmf::advance_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);  // fusion of u-1 + setup of u
@@ -462,12 +449,12 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
         CUX(cudaMalloc(&c->d_units_tail, np * (dmf::CHUNK - 1) * sizeof(unsigned int)));
         CUX(cudaMalloc(&c->d_ctrl, 3 * sizeof(dmf::Ctrl)));
         for (int b = 0; b < 2; ++b) {
-            c->tab_bytes = W * H * (sizeof(int4) + sizeof(dmf::currx_t) + sizeof(dmf::mom2_t));
-            CUX(cudaMalloc(&c->d_tab[b], c->tab_bytes));
-            c->d_mom1[b] = static_cast<int4 *>(c->d_tab[b]);
-            c->d_currx[b] = reinterpret_cast<dmf::currx_t *>(c->d_mom1[b] + W * H);
-            c->d_mom2[b] = reinterpret_cast<dmf::mom2_t *>(c->d_currx[b] + W * H);
-            CUX(cudaMemsetAsync(c->d_tab[b], 0, c->tab_bytes, c->stream));
+            CUX(cudaMalloc(&c->d_mom1[b], W * H * sizeof(int4)));
+            CUX(cudaMalloc(&c->d_mom2[b], W * H * sizeof(dmf::mom2_t)));
+            CUX(cudaMalloc(&c->d_currx[b], W * H * sizeof(dmf::currx_t)));
+            CUX(cudaMemsetAsync(c->d_mom1[b], 0, W * H * sizeof(int4), c->stream));
+            CUX(cudaMemsetAsync(c->d_mom2[b], 0, W * H * sizeof(dmf::mom2_t), c->stream));
+            CUX(cudaMemsetAsync(c->d_currx[b], 0, W * H * sizeof(dmf::currx_t), c->stream));
             CUX(cudaEventCreateWithFlags(&c->ev_mom_done[b], cudaEventDisableTiming));
             CUX(cudaEventCreateWithFlags(&c->ev_tab_free[b], cudaEventDisableTiming));
             CUX(cudaEventCreateWithFlags(&c->ev_adv_done[b], cudaEventDisableTiming));
@@ -498,25 +485,6 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             if (carve >= 0) {
                 CUX(cudaFuncSetAttribute(c->ncc_fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
                 CUX(cudaFuncSetAttribute(dmf::moments_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            }
-        }
-        if (const char *lp = std::getenv("DMF_L2_PERSIST")) {
-            // L2 residency control: the moment tables of the running update are read ~10x each in random order by ncc_kernel
-            // while records, units and maps stream through once; ask L2 to keep the former (persisting) and to treat misses
-            // outside the set-aside as streaming.  DMF_L2_PERSIST = fraction of the device's maximum set-aside to use.
-            const double frac = std::atof(lp);
-            int max_persist = 0, max_window = 0;
-            CUX(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
-            CUX(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
-            if (frac > 0 && max_persist > 0 && max_window > 0) {
-                const size_t want = (size_t)(frac * max_persist);
-                CUX(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-                const size_t win = c->tab_bytes < (size_t)max_window ? c->tab_bytes : (size_t)max_window;
-                const double r = (double)want / (double)win;
-                c->l2_hit_ratio = (float)(r < 1.0 ? r : 1.0);
-                if (std::getenv("DMF_VERBOSE"))
-                    std::fprintf(stderr, "dmf: L2 persisting set-aside %zu of max %d B, window max %d B, tables %zu B, hit ratio %.2f\n", want,
-                                 max_persist, max_window, c->tab_bytes, c->l2_hit_ratio);
             }
         }
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ncc_fn, dmf::NCC_THREADS, 0));
@@ -581,7 +549,7 @@ void dmf_destroy(dmf_ctx *ctx) {
     for (int b = 0; b < 2; ++b) { cudaFree(ctx->d_rec[b]); cudaFree(ctx->d_best[b]); cudaFree(ctx->d_state_c[b]); }
     cudaFree(ctx->d_units_full); cudaFree(ctx->d_units_tail); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_cta_cnt); cudaFree(ctx->d_refx);
     for (int b = 0; b < 2; ++b) {
-        cudaFree(ctx->d_tab[b]);
+        cudaFree(ctx->d_mom1[b]); cudaFree(ctx->d_mom2[b]); cudaFree(ctx->d_currx[b]);
         if (ctx->ev_mom_done[b]) cudaEventDestroy(ctx->ev_mom_done[b]);
         if (ctx->ev_tab_free[b]) cudaEventDestroy(ctx->ev_tab_free[b]);
         if (ctx->ev_adv_done[b]) cudaEventDestroy(ctx->ev_adv_done[b]);

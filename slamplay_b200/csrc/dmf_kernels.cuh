@@ -69,15 +69,6 @@ constexpr int CHUNK_BITS = 6;     // unit = (pixel index << CHUNK_BITS) | chunk 
 #ifndef DMF_NCC_THREADS
 #define DMF_NCC_THREADS 192
 #endif
-#ifndef DMF_NCC_PIPE
-#define DMF_NCC_PIPE 0             // 1: the loads of sample j+1 are issued before sample j is reduced (two samples in flight per thread)
-#endif
-#ifndef DMF_NCC_GRAB_AHEAD
-#define DMF_NCC_GRAB_AHEAD 0       // 1: a warp claims its next grab while it works on the current one and prefetches those records into L2
-#endif
-#ifndef DMF_NCC_SB_EXTRA_BLOCKS
-#define DMF_NCC_SB_EXTRA_BLOCKS 1  // the SHIFT_BLOCK variant is compiled for this many more CTAs per SM
-#endif
 #ifndef DMF_NCC_MIN_BLOCKS
 #define DMF_NCC_MIN_BLOCKS 3
 #endif
@@ -584,7 +575,11 @@ __device__ __forceinline__ void load_raw(const KParams &P, int ix, int iy, RawSa
 // Measured and dropped (bit-identical results, slower): prefetching the next sample's lines (CCTL.PF1, +34 %:
 // profiles/r02_ab_ncc_prefetch_and_moments.txt, commit 04641b5) and carrying moment-table entries between neighbouring
 // integer positions in registers (the per-lane step-type branches serialise the loads, +28 %: profiles/r02_ab_ncc_carry.txt,
-// commit 43954c3).  The kernel is bound by L1 wavefronts (bytes) and by the latency of L1 misses, not by load instructions.
+// commit 43954c3); two samples in flight per thread (operands of sample j+1 requested before sample j is reduced: 128-168
+// registers, 12-16 warps/SM, +36..60 %: profiles/r02_ab_ncc_two_samples_in_flight.txt); an L2 persisting window on the
+// moment tables (no change) and claiming the next grab early with an L2 prefetch of its records (+3 %:
+// profiles/r02_ab_l2_persist_and_grab_ahead.txt; all three in commit c87ba67).  Throughput follows the number of resident
+// warps: the kernel is bound by L1 wavefronts and by dependent-issue latency, not by DRAM latency or load instructions.
 // cross sums with the reference patch (window (a,b) = block columns a..a+6, rows b..b+6) + exact int32 centring.
 // SHIFT_BLOCK: the windows a = 1 (block columns 1..7) are formed by shifting the BLOCK row by one byte per sample
 // (2 ALU ops per row) instead of holding a second, byte-shifted copy of the reference patch (14 registers less: 80
@@ -659,7 +654,7 @@ __device__ __forceinline__ void fetch_units(const KParams &P, const unsigned (&c
 }
 
 template <int WIDTH, bool SHIFT_BLOCK>
-__global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS + DMF_NCC_SB_EXTRA_BLOCKS : DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS + 1 : DMF_NCC_MIN_BLOCKS) ncc_kernel(const __grid_constant__ KParams P) {
     const int lane = threadIdx.x & 31;
     // padded, concatenated lists: length CHUNK first, then CHUNK-1, ..., 1; each segment 32-aligned
     unsigned counts[CHUNK + 1];
@@ -671,32 +666,7 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
     }
     unsigned my_evals = 0;
 
-#if DMF_NCC_GRAB_AHEAD
-    auto claim = [&]() {
-        unsigned g = 0;
-        if (lane == 0) g = atomicAdd(&P.ctrl->cursor, (unsigned)GRAB);
-        return __shfl_sync(0xffffffffu, g, 0);
-    };
-    unsigned g_next = claim();
-    unsigned units_next[GRAB / 32];
-    int lens_next[GRAB / 32];
-    if (g_next < total) fetch_units(P, counts, total, g_next, lane, units_next, lens_next);
-#endif
     for (;;) {
-#if DMF_NCC_GRAB_AHEAD
-        if (g_next >= total) break;
-        unsigned units[GRAB / 32];
-        int lens[GRAB / 32];
-#pragma unroll
-        for (int sub = 0; sub < GRAB / 32; ++sub) { units[sub] = units_next[sub]; lens[sub] = lens_next[sub]; }
-        g_next = claim();
-        if (g_next < total) {
-            fetch_units(P, counts, total, g_next, lane, units_next, lens_next);
-#pragma unroll
-            for (int sub = 0; sub < GRAB / 32; ++sub)
-                if (lens_next[sub]) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rec + (units_next[sub] >> CHUNK_BITS)));
-        }
-#else
         unsigned g = 0;
         if (lane == 0) g = atomicAdd(&P.ctrl->cursor, (unsigned)GRAB);
         g = __shfl_sync(0xffffffffu, g, 0);
@@ -705,7 +675,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
         unsigned units[GRAB / 32];
         int lens[GRAB / 32];
         fetch_units(P, counts, total, g, lane, units, lens);
-#endif
 #pragma unroll
         for (int sub = 0; sub < GRAB / 32; ++sub) {
             const int L = lens[sub];
@@ -747,56 +716,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
             double l = dmf_geom::sample_l_acc(half, P.step, k0);
             sx = __dadd_rn(pm.x, __dmul_rn(l, dir.x));  // ref:433, unfused like the reference build
             sy = __dadd_rn(pm.y, __dmul_rn(l, dir.y));
-#if DMF_NCC_PIPE
-            // Two samples in flight: the operands of sample j+1 are requested before sample j is reduced and combined,
-            // into the other of two register sets (the loop is unrolled by two so that the sets swap roles statically).
-            struct Located { bool ok, load; int ix, iy; double fx, fy; };
-            auto locate = [&](double cx, double cy, Located &s) {
-                s.ok = cx >= P.bd && cy >= P.bd && cx + P.bd < P.wd && cy + P.bd <= P.hd;  // inside() ref:222-224
-                s.load = false;
-                if (s.ok) {
-                    split_coord(cx, s.ix, s.fx);
-                    split_coord(cy, s.iy, s.fy);
-                    s.load = s.ix != hix || s.iy != hiy;
-                    if (s.load) { hix = s.ix; hiy = s.iy; }  // position of the most recent request
-                }
-            };
-            auto next_pos = [&]() {
-                l = __dadd_rn(l, P.step);
-                sx = __dadd_rn(pm.x, __dmul_rn(l, dir.x));
-                sy = __dadd_rn(pm.y, __dmul_rn(l, dir.y));
-            };
-            auto finish = [&](const Located &s, const RawSample &raw, int k) {
-                if (s.load) si = reduce_raw<SHIFT_BLOCK>(raw, R0lo, R0hi, R1lo, R1hi, nSr);
-                if (s.ok) {
-                    const double v = ncc_combine(si, den1, s.fx, s.fy);
-                    ++my_evals;
-                    if (v > best_v) { best_v = v; best_k = k; }  // first strict maximum ref:438-441
-                }
-            };
-            RawSample rawA, rawB;
-            Located a, b;
-            locate(sx, sy, a);
-            if (a.load) load_raw<WIDTH>(P, a.ix, a.iy, rawA);
-#pragma unroll 1
-            for (int j = 0; j < L; j += 2) {
-                b.ok = false; b.load = false;
-                if (j + 1 < L) {
-                    next_pos();
-                    locate(sx, sy, b);
-                    if (b.load) load_raw<WIDTH>(P, b.ix, b.iy, rawB);
-                }
-                finish(a, rawA, k0 + j);
-                if (j + 1 >= L) break;
-                a.ok = false; a.load = false;
-                if (j + 2 < L) {
-                    next_pos();
-                    locate(sx, sy, a);
-                    if (a.load) load_raw<WIDTH>(P, a.ix, a.iy, rawA);
-                }
-                finish(b, rawB, k0 + j + 1);
-            }
-#else
 #pragma unroll 1
             for (int j = 0; j < L; ++j) {
                 const double cx = sx, cy = sy;
@@ -820,7 +739,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
                 ++my_evals;
                 if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
-#endif
             if (best_k >= 0) atomicMax(&P.best[slot], ncc_key(best_v, best_k));
         }
     }
