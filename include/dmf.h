@@ -101,7 +101,9 @@ int dmf_create(const dmf_params *params, int device, int row_begin, int row_end,
  * Block-cyclic row ownership for multi-GPU runs (SURVEY.md 8e "fallback if contiguous bands do not
  * balance"): the interior rows are cut into blocks of `block_rows` rows, dealt to `n_parts`
  * contexts in boustrophedon order (0..n-1, n-1..0, ...); this context is number `part`.  Convergence varies smoothly down the image, so interleaved
- * blocks give every GPU the same mix of short and long epipolar searches.  Upload / download move the
+ * blocks give every GPU the same mix of short and long epipolar searches.  An incomplete last round is dealt from
+ * context n-1 down whatever its parity (the rows next to the image border converge last: the context that holds the
+ * first block of the image does not also get an extra block at the bottom).  Upload / download move the
  * owned rows only.  dmf_get_rows lists the owned image rows in local order (rows_out may be NULL to
  * query the count).
  */

@@ -22,6 +22,7 @@ struct dmf_ctx_impl {
     int device = 0;
     // rows owned: local row rl -> image row  row0 + ((rl / blk) * cyc + ph) * blk + rl % blk
     int row0 = 0, blk = 1, cyc = 1, ph = 0, n_rows = 0;
+    int rev_round = -1;  // incomplete last round of a block-cyclic dealing (dealt in reverse), or -1
     std::vector<std::pair<int, int>> spans;     // owned interior rows as ascending [y0, y1) intervals
     std::vector<std::pair<int, int>> io_spans;  // rows moved by upload / download (spans, plus border rows a contiguous band asked for)
     // stream: advance (fusion + set-up) -> ncc of every update; mom_stream: moments_kernel of the NEXT update runs beside them
@@ -136,7 +137,7 @@ void fill_kparams(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long u) {
     const dmf_params &p = c->prm;
     const int b = (int)(u & 1);  // parity of update u: slot buffers and moment-table buffer
     K.width = p.width; K.height = p.height; K.border = p.border;
-    K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows;
+    K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows; K.rev_round = c->rev_round;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
     K.ncc_thresh = p.ncc_thresh;
     K.fx = p.fx; K.fy = p.fy; K.cx = p.cx; K.cy = p.cy;
@@ -370,8 +371,13 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             c->row0 = lo; c->blk = block_rows; c->cyc = n_parts; c->ph = part; c->n_rows = 0;
             // round k deals blocks k*n_parts .. k*n_parts + n_parts-1; odd rounds in reverse order (boustrophedon).
             // Only the last block of the image can be short, and a context's rounds stop at its first missing block.
+            // An incomplete last round is dealt from the highest context down whatever its parity: the rows next to
+            // the image border converge last (their matches leave the frame), so the context that holds the first
+            // block should not also receive an extra last one (measured at 1080p / 8 contexts: 1.20x -> the mean load).
+            const int n_blocks = (hi - lo + block_rows - 1) / block_rows;
+            c->rev_round = (n_blocks % n_parts) ? n_blocks / n_parts : -1;
             for (int k = 0;; ++k) {
-                const int pos = (k & 1) ? (n_parts - 1 - part) : part;
+                const int pos = ((k & 1) || k == c->rev_round) ? (n_parts - 1 - part) : part;
                 const int y0 = lo + (k * n_parts + pos) * block_rows;
                 if (y0 >= hi) break;
                 const int y1 = (y0 + block_rows < hi) ? y0 + block_rows : hi;

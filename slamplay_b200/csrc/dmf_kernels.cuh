@@ -114,6 +114,7 @@ struct KParams {
     //  varies linearly down the image splits evenly; this context is number `ph`;
     //  a contiguous band is blk = n_rows, cyc = 1, ph = 0).
     int row0, blk, cyc, ph, n_rows;
+    int rev_round;  // index of the incomplete last round (dealt from the highest context down whatever its parity), or -1
     int wi;                  // width - 2*border
     int n_pix;               // interior pixels owned = wi * n_rows
     int inverse_depth;
@@ -170,7 +171,7 @@ __device__ __forceinline__ double int2double_fast(int k) {
 }
 __device__ __forceinline__ int row_of(const KParams &P, int rl) {
     const int b = rl / P.blk;
-    const int pos = (b & 1) ? (P.cyc - 1 - P.ph) : P.ph;
+    const int pos = ((b & 1) || b == P.rev_round) ? (P.cyc - 1 - P.ph) : P.ph;
     return P.row0 + (b * P.cyc + pos) * P.blk + (rl - b * P.blk);
 }
 // arg-max key: ncc in [-1,1] -> ncc + 3.0 in [2,4): the 52 mantissa bits are an order-preserving

@@ -41,8 +41,10 @@ def cyclic_rows(height: int, border: int, block_rows: int, world: int, rank: int
     lo, hi = border, height - border
     rows = []
     k = 0
+    n_blocks = -(-(hi - lo) // block_rows)
+    rev_round = n_blocks // world if n_blocks % world else -1  # an incomplete last round is dealt from the highest rank down
     while True:  # round k deals blocks k*world .. k*world + world-1, odd rounds in reverse (boustrophedon)
-        pos = (world - 1 - rank) if (k & 1) else rank
+        pos = (world - 1 - rank) if ((k & 1) or k == rev_round) else rank
         y0 = lo + (k * world + pos) * block_rows
         if y0 >= hi:
             break

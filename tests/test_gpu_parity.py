@@ -260,15 +260,19 @@ def test_band_contexts_are_bit_identical_to_one_context(DF, seq640):
     assert all(tot[k] == cw[k] for k in tot)
 
 
-def test_cyclic_contexts_are_bit_identical_to_one_context(DF, seq640):
+@pytest.mark.parametrize("blk", [16, 8])  # 28 blocks: the incomplete last round is odd; 55 blocks: even (dealt in reverse too)
+def test_cyclic_contexts_are_bit_identical_to_one_context(DF, seq640, blk):
     """Block-cyclic row ownership (dmf_create_cyclic): three interleaved contexts == one context."""
+    from slamplay_b200.sharded import cyclic_rows
     seq, frames = seq640
     p = seq.params
     h, w = seq.shape
     whole = DF(p)
-    parts = [DF(p, cyclic=(16, 3, r)) for r in range(3)]
+    parts = [DF(p, cyclic=(blk, 3, r)) for r in range(3)]
     rows = np.concatenate([f.owned_rows() for f in parts])
     assert sorted(rows.tolist()) == list(range(p.border, h - p.border))
+    for r, f in enumerate(parts):  # the host-side replica of the dealing rule (gather / scatter of the sharded filter)
+        assert np.array_equal(np.sort(f.owned_rows()), cyclic_rows(h, p.border, blk, 3, r))
     for f in [whole] + parts:
         f.set_reference(frames[0])
         f.fill_state(3.0, 3.0)

@@ -32,6 +32,19 @@ def test_cyclic_rows_partition_the_interior():
             assert sorted(allr.tolist()) == list(range(b, h - b))
 
 
+def test_cyclic_rows_incomplete_last_round_goes_to_the_high_ranks():
+    # 1080p, 8 ranks: 130 blocks = 16 rounds + 2 blocks; round 16 is even but dealt in reverse, so rank 0 (which holds the
+    # first block of the image) does not also receive an extra block next to the bottom border
+    rows = [cyclic_rows(1080, 20, 8, 8, r) for r in range(8)]
+    n = [len(r) // 8 for r in rows]
+    assert n == [16, 16, 16, 16, 16, 16, 17, 17]
+    assert rows[7][-1] == 1080 - 20 - 8 - 1 and rows[6][-1] == 1080 - 20 - 1
+    # 4K, 8 ranks: 33 rounds + 1 block; round 33 is odd, reverse anyway
+    assert [len(cyclic_rows(2160, 20, 8, 8, r)) // 8 for r in range(8)] == [33] * 7 + [34]
+    # complete rounds only: plain boustrophedon
+    assert cyclic_rows(20 + 8 * 16 + 20, 20, 8, 8, 0).tolist() == list(range(20, 28)) + list(range(20 + 15 * 8, 20 + 16 * 8))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

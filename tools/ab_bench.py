@@ -31,8 +31,10 @@ for spec in libs:
     _lib._cache.pop("dmf", None)
     try:
         # DMF_AB_CYCLIC=N: the context of rank 0 of an N-GPU run (1/N of the rows, whole-frame moment table)
+        # DMF_AB_BLOCK_ROWS / DMF_AB_PART: rows per cyclic block (default 8) and which rank's share (default 0)
         ncyc = int(os.environ.get("DMF_AB_CYCLIC", "0"))
-        f = DepthFilter(seq.params, device=0, cyclic=(8, ncyc, 0)) if ncyc > 1 else DepthFilter(seq.params, device=0)
+        brows, part = int(os.environ.get("DMF_AB_BLOCK_ROWS", "8")), int(os.environ.get("DMF_AB_PART", "0"))
+        f = DepthFilter(seq.params, device=0, cyclic=(brows, ncyc, part)) if ncyc > 1 else DepthFilter(seq.params, device=0)
         f.set_reference_device(frames[0].data_ptr(), pitch)
         st = torch.cuda.ExternalStream(f.stream())
         best = 1e9
