@@ -68,6 +68,12 @@ struct dmf_ctx_impl {
     uint2 *d_refx = nullptr;                   // expanded reference frame (ref_expand_kernel)
     int n_pix = 0, ncc_grid = 0;
     bool mom_bulk = true;                      // moments_bulk_kernel (DMF_MOMENTS=legacy selects moments_kernel: A/B runs)
+    // DMF_TRACE=<file> (diagnostic): %globaltimer stamps on the streams around the three kernels of every update,
+    // written to <file> by dmf_destroy: when does moments(u) run relative to ncc(u-1)?
+    unsigned long long *d_trace = nullptr;
+    int trace_cap = 0;
+    std::string trace_path;
+    int mom_repeat = 1;                        // DMF_MOMENTS_REPEAT (diagnostic): launches per update; the extra time per update is the exposed cost of one
     int mom_grid = 296;                        // persistent CTAs of moments_bulk_kernel (DMF_MOMENTS_CTAS_PER_SM x SMs)
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
     // optional per-kernel timing (dmf_set_timing): 5 events per update bracket the 4 timing slots
@@ -193,6 +199,12 @@ int flush_pending(dmf_ctx_impl *c) {
     return DMF_OK;
 }
 
+__global__ void stamp_kernel(unsigned long long *dst) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *dst = t;
+}
+
 // frame_ready: event after which the frame at d_curr is complete (NULL: it already is when this call is made).
 int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const double q[4], const double t[3],
                   cudaEvent_t frame_ready, cudaEvent_t frame_consumed) {
@@ -235,11 +247,15 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             // registers that kernel leaves free
             if (c->mom_gate && u > 0) CU(cudaStreamWaitEvent(ms, c->ev_adv_done[b ^ 1], 0));
         }
+        unsigned long long *tr = (c->d_trace && u < (unsigned long long)c->trace_cap) ? c->d_trace + 6 * u : nullptr;
+        if (tr) { stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 0); stamp_kernel<<<1, 1, 0, ms>>>(tr + 2); }
         if (ev[0]) CU(cudaEventRecord(ev[0], c->stream));
         if (merged) dmf::advance_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);  // fusion of u-1 + setup of u
         else dmf::setup_kernel<<<grid, dmf::TILE_PIX, 0, c->stream>>>(K);
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
+        if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 1);
         CU(cudaEventRecord(c->ev_adv_done[b], c->stream));
+        for (int rep = 0; rep < c->mom_repeat; ++rep)
         if (c->mom_bulk && (reinterpret_cast<uintptr_t>(d_curr) & 15u) == 0 && (curr_pitch & 15) == 0) {
             // tiles staged in shared memory by bulk asynchronous copies: efficient at the one-CTA-per-SM occupancy that is
             // left beside the persistent ncc_kernel of the previous update
@@ -251,13 +267,16 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         } else {
             dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
         }
+        if (tr) stamp_kernel<<<1, 1, 0, ms>>>(tr + 3);
         if (frame_consumed) CU(cudaEventRecord(frame_consumed, ms));
         if (ms != c->stream) {
             CU(cudaEventRecord(c->ev_mom_done[b], ms));
             CU(cudaStreamWaitEvent(c->stream, c->ev_mom_done[b], 0));
         }
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
+        if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 4);
         c->ncc_fn<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
+        if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 5);
         CU(cudaEventRecord(c->ev_tab_free[b], c->stream));
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
         CU(cudaGetLastError());
@@ -504,6 +523,13 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             c->mom_bulk = mm ? std::strcmp(mm, "legacy") != 0 : (size_t)params->width * params->height >= (1u << 20);
             const char *mg = std::getenv("DMF_MOMENTS_GATE");
             c->mom_gate = !(mg && std::strcmp(mg, "0") == 0);
+            if (const char *tp = std::getenv("DMF_TRACE")) {
+                c->trace_path = tp;
+                c->trace_cap = 1024;
+                CUX(cudaMalloc(&c->d_trace, (size_t)c->trace_cap * 6 * sizeof(unsigned long long)));
+                CUX(cudaMemset(c->d_trace, 0, (size_t)c->trace_cap * 6 * sizeof(unsigned long long)));
+            }
+            if (const char *mr = std::getenv("DMF_MOMENTS_REPEAT")) c->mom_repeat = std::atoi(mr) > 1 ? std::atoi(mr) : 1;
             int k = mc ? std::atoi(mc) : 2;
             if (k < 1) k = 1;
             c->mom_grid = prop.multiProcessorCount * k;
@@ -539,6 +565,17 @@ void dmf_destroy(dmf_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->mom_stream) cudaStreamSynchronize(ctx->mom_stream);
+    if (ctx->d_trace) {
+        std::vector<unsigned long long> h((size_t)ctx->trace_cap * 6);
+        if (cudaMemcpy(h.data(), ctx->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+            if (FILE *f = std::fopen(ctx->trace_path.c_str(), "w")) {
+                std::fprintf(f, "# update advance_begin advance_end moments_eligible moments_end ncc_begin ncc_end   (ns, %%globaltimer)\n");
+                for (int u = 0; u < ctx->trace_cap && h[6 * (size_t)u]; ++u)
+                    std::fprintf(f, "%d %llu %llu %llu %llu %llu %llu\n", u, h[6 * u], h[6 * u + 1], h[6 * u + 2], h[6 * u + 3], h[6 * u + 4], h[6 * u + 5]);
+                std::fclose(f);
+            }
+        cudaFree(ctx->d_trace);
+    }
     cudaFree(ctx->d_ref);
     for (int b = 0; b < 2; ++b) {
         cudaFree(ctx->d_curr[b]);
