@@ -73,11 +73,6 @@ struct dmf_ctx_impl {
     unsigned long long *d_trace = nullptr;
     int trace_cap = 0;
     std::string trace_path;
-    // Row-masked tables (contexts of a split over >= 4 parts, DMF_MOMENTS_MASK=0|1 forces): advance / setup mark the table
-    // rows this update's searches can read, the moments kernel runs AFTER them on the context stream and stores only those.
-    bool mom_mask = false;
-    unsigned *d_row_mask = nullptr;
-    int mask_words = 0;
     int mom_repeat = 1;                        // DMF_MOMENTS_REPEAT (diagnostic): launches per update; the extra time per update is the exposed cost of one
     int mom_grid = 296;                        // persistent CTAs of moments_bulk_kernel (DMF_MOMENTS_CTAS_PER_SM x SMs)
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
@@ -148,7 +143,6 @@ void fill_kparams(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long u) {
     const dmf_params &p = c->prm;
     const int b = (int)(u & 1);  // parity of update u: slot buffers and moment-table buffer
     K.width = p.width; K.height = p.height; K.border = p.border;
-    K.row_mask = c->mom_mask ? c->d_row_mask : nullptr; K.mask_words = c->mask_words;
     K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows; K.rev_round = c->rev_round;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
     K.ncc_thresh = p.ncc_thresh;
@@ -244,11 +238,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         // moments_kernel needs only the frame, not the state: it runs on its own stream, beside setup / ncc / fuse of
         // the PREVIOUS update (whose ncc_kernel reads the other table buffer).  With per-kernel timing on, everything
         // is serialised on the context stream so that the event pairs bracket one kernel each.
-        // Row-masked tables (mom_mask): the kernel depends on this update's advance / setup, so it follows them on the
-        // context stream; it then writes only the rows that are read (it is bound by its table writes).
-        cudaStream_t ms = (c->timing_on || c->mom_mask) ? c->stream : c->mom_stream;
+        cudaStream_t ms = c->timing_on ? c->stream : c->mom_stream;
+        if (frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));
         if (ms != c->stream) {
-            if (frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));
             CU(cudaStreamWaitEvent(ms, c->ev_tab_free[b], 0));  // ncc_kernel of two updates ago has released the table buffer
             // ... and not before the ncc_kernel of the PREVIOUS update is released: beside advance_kernel (which fills every
             // register file) the precompute would only take its place in the queue; beside ncc_kernel it runs in the
@@ -263,7 +255,6 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         if (ev[1]) CU(cudaEventRecord(ev[1], c->stream));
         if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 1);
         CU(cudaEventRecord(c->ev_adv_done[b], c->stream));
-        if (ms == c->stream && frame_ready) CU(cudaStreamWaitEvent(ms, frame_ready, 0));  // advance / setup did not need the frame
         for (int rep = 0; rep < c->mom_repeat; ++rep)
         if (c->mom_bulk && (reinterpret_cast<uintptr_t>(d_curr) & 15u) == 0 && (curr_pitch & 15) == 0) {
             // tiles staged in shared memory by bulk asynchronous copies: efficient at the one-CTA-per-SM occupancy that is
@@ -272,9 +263,9 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
             const int n_tiles = tiles_x * tiles_y;
             const int grid_b = n_tiles < c->mom_grid ? n_tiles : c->mom_grid;
             dmf::moments_bulk_kernel<<<grid_b, dmf::MB_COLS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width,
-                                                                      c->d_currx[b], tiles_x, n_tiles, K.row_mask);
+                                                                      c->d_currx[b], tiles_x, n_tiles);
         } else {
-            dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b], K.row_mask);
+            dmf::moments_kernel<<<mgrid, dmf::MOM_THREADS, 0, ms>>>(d_curr, curr_pitch, p.width, p.height, c->d_mom1[b], c->d_mom2[b], p.width, c->d_currx[b]);
         }
         if (tr) stamp_kernel<<<1, 1, 0, ms>>>(tr + 3);
         if (frame_consumed) CU(cudaEventRecord(frame_consumed, ms));
@@ -532,13 +523,6 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             c->mom_bulk = mm ? std::strcmp(mm, "legacy") != 0 : (size_t)params->width * params->height >= (1u << 20);
             const char *mg = std::getenv("DMF_MOMENTS_GATE");
             c->mom_gate = !(mg && std::strcmp(mg, "0") == 0);
-            {
-                const char *mk = std::getenv("DMF_MOMENTS_MASK");
-                c->mom_mask = mk ? std::atoi(mk) != 0 : n_parts >= 4;
-                c->mask_words = (int)((H + 31) / 32);
-                CUX(cudaMalloc(&c->d_row_mask, (size_t)(c->mask_words + 1) * sizeof(unsigned)));  // + the padding word needed_rows reads
-                CUX(cudaMemsetAsync(c->d_row_mask, 0, (size_t)(c->mask_words + 1) * sizeof(unsigned), c->stream));
-            }
             if (const char *tp = std::getenv("DMF_TRACE")) {
                 c->trace_path = tp;
                 c->trace_cap = 1024;
@@ -581,7 +565,6 @@ void dmf_destroy(dmf_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->mom_stream) cudaStreamSynchronize(ctx->mom_stream);
-    cudaFree(ctx->d_row_mask);
     if (ctx->d_trace) {
         std::vector<unsigned long long> h((size_t)ctx->trace_cap * 6);
         if (cudaMemcpy(h.data(), ctx->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)

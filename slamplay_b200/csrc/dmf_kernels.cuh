@@ -113,11 +113,6 @@ struct KParams {
     // (block-cyclic: blocks of `blk` rows dealt to `cyc` contexts in boustrophedon order, so a load that
     //  varies linearly down the image splits evenly; this context is number `ph`;
     //  a contiguous band is blk = n_rows, cyc = 1, ph = 0).
-    // Rows of the current frame's tables that this update's searches can read (bit y of word y / 32), or NULL: every
-    // row.  Written by emit_pixel (hull of the CTA's epipolar segments), read by the moments kernels (rows outside are
-    // computed but not STORED: the kernels are bound by their 28 B/px of table writes), cleared by ncc_kernel.
-    unsigned *row_mask;
-    int mask_words;
     int row0, blk, cyc, ph, n_rows;
     int rev_round;  // index of the incomplete last round (dealt from the highest context down whatever its parity), or -1
     int wi;                  // width - 2*border
@@ -264,22 +259,7 @@ __device__ __forceinline__ void prepare_pixel(const KParams &P, PixelWork &w, bo
 __device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w, bool accepted = false, unsigned n_fin = 0) {
     __shared__ unsigned s_cnt[TILE_PIX / 32][CHUNK + 2];   // [warp][L]: units of length L (L == CHUNK: full units); [warp][0]: active pixels
     __shared__ unsigned s_base[TILE_PIX / 32][CHUNK + 1];  // first entry of that warp in list L / first slot
-    __shared__ int s_rows[TILE_PIX / 32][2];               // [warp]: first / last table row its searches can read
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (P.row_mask) {
-        // samples lie on pm + l*dir, |l| <= half (ref:432-433); a sample at (.,cy) reads table rows floor(cy)-3 .. floor(cy)+4
-        // (load_raw); one row of slack on each side for the rounding of the accumulated l.  inside() (ref:222-224) keeps
-        // floor(cy) within [border, height - border].  NaN bounds select every row.
-        int lo = 0x7fffffff, hi = -1;
-        if (w.active && w.n > 0) {
-            const double r = fabs(w.half * w.ly);
-            const double a = fmax(w.pmy - r, (double)P.border), b = fmin(w.pmy + r, (double)(P.height - P.border));
-            if (a <= b || a != a || b != b) { lo = max((int)a - 4, 0); hi = min((int)b + 5, P.height - 1); }
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) { s_rows[warp][0] = lo; s_rows[warp][1] = hi; }
-    }
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_full = w.n / CHUNK, tail = w.n % CHUNK;
     const int tot_full = __reduce_add_sync(0xffffffffu, n_full);
@@ -304,14 +284,6 @@ __device__ __forceinline__ void emit_pixel(const KParams &P, const PixelWork &w,
         else base = tot ? atomicAdd(&P.ctrl->count[tid], tot) : 0u;
 #pragma unroll
         for (int k = 0; k < TILE_PIX / 32; ++k) s_base[k][tid] = base + pre[k];
-    } else if (tid == CHUNK + 2 && P.row_mask) {  // the CTA's hull of table rows -> one atomicOr per 32 rows
-        int lo = 0x7fffffff, hi = -1;
-#pragma unroll
-        for (int k = 0; k < TILE_PIX / 32; ++k) { lo = min(lo, s_rows[k][0]); hi = max(hi, s_rows[k][1]); }
-        for (int wd = lo >> 5; wd <= (hi >> 5); ++wd) {  // empty when no pixel of the CTA searches (hi = -1)
-            const int b0 = max(lo - wd * 32, 0), b1 = min(hi - wd * 32, 31);
-            atomicOr(&P.row_mask[wd], (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0));
-        }
     } else if (tid == CHUNK + 1 && n_fin) {  // counters of the finished frame: active, accepted
         unsigned acc = 0;
 #pragma unroll
@@ -409,19 +381,11 @@ __device__ __forceinline__ PairSums pair_sums(const RowBytes &a, const RowBytes 
             dp4(a.x1l, b.x0l, dp4(a.x1h, b.x0h, 0))};
 }
 
-// Bit i of the result = row y0 + i of the tables is read by this update (KParams::row_mask; NULL: every row).
-__device__ __forceinline__ unsigned long long needed_rows(const unsigned *__restrict__ row_mask, int y0) {
-    if (!row_mask) return ~0ull;
-    const unsigned lo = __ldg(row_mask + (y0 >> 5)), hi = __ldg(row_mask + (y0 >> 5) + 1);  // one padding word follows the mask
-    return (((unsigned long long)hi << 32) | lo) >> (y0 & 31);
-}
 // One column x, positions y0 .. y_end-1: wp = the 4-byte aligned word that holds byte (x, y0), pw = words per row,
-// sh = 8 * (byte offset of x inside that word).  Rows up to min(y_end + 8, height - 1) are read.  Rows whose bit in
-// `need` (needed_rows(.., y0)) is clear are slid over but not stored.
+// sh = 8 * (byte offset of x inside that word).  Rows up to min(y_end + 8, height - 1) are read.
 template <bool SMEM>
 __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsigned sh, int x, int y0, int y_end, int width, int height,
-                                              int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch, currx_t *__restrict__ currx,
-                                              unsigned long long need) {
+                                              int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch, currx_t *__restrict__ currx) {
     // window state for position y0: single-row sums over rows y0..y0+6, pair sums over (y0,y0+1)..(y0+6,y0+7)
     int S0 = 0, S1 = 0, Q = 0, H = 0, V = 0, D1 = 0, D2 = 0;
     RowBytes prev = load_row_bytes<SMEM>(wp, sh);
@@ -447,14 +411,12 @@ __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsign
         a.z = NCC_AREA * H - S0 * S1;
         a.w = NCC_AREA * V - S0 * S0n;
         const int bx = NCC_AREA * D1 - S0 * S1n, by = NCC_AREA * D2 - S1 * S0n;
-        if ((need >> (y - y0)) & 1ull) {
-            mom1[(size_t)y * mom_pitch + x] = a;
-            mom2[(size_t)y * mom_pitch + x] = bx + by;  // |bx|, |by| < 2^30: exact
-            // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
-            // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
-            // funnel shifts
-            currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
-        }
+        mom1[(size_t)y * mom_pitch + x] = a;
+        mom2[(size_t)y * mom_pitch + x] = bx + by;  // |bx|, |by| < 2^30: exact
+        // by-product, "sliding window expansion": the 8 bytes [x, x+8) of row y as one aligned 64-bit word, so
+        // that a sample fetches each row of its 8x8 block with ONE aligned LDG.64 instead of three LDG.32 + two
+        // funnel shifts
+        currx[(size_t)y * width + x] = make_uint2(old_a.x0l, old_a.hi);
         // advance the window to position y+1
         S0 = S0n; S1 = S1n;
         Q += rn.q - ro.q; H += rn.h - ro.h;
@@ -468,17 +430,15 @@ __device__ __forceinline__ void moments_strip(const uint32_t *wp, int pw, unsign
 
 __global__ void __launch_bounds__(MOM_THREADS) moments_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                       int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                      currx_t *__restrict__ currx, const unsigned *__restrict__ row_mask) {
+                                                      currx_t *__restrict__ currx) {
     const int x = blockIdx.x * MOM_THREADS + threadIdx.x;
     const int y0 = blockIdx.y * MOM_STRIP;
     const int y_end = min(y0 + MOM_STRIP, height - 8);  // positions y0 .. y_end-1 ; rows up to y+8 are read
     if (x > width - 16 || y0 >= y_end) return;  // x <= W-16: the 12-byte row reads stay inside the row
-    const unsigned long long need = needed_rows(row_mask, y0);
-    if (!(need << (64 - MOM_STRIP))) return;    // none of the strip's rows is read by this update
     const uint8_t *base = img + (size_t)y0 * pitch + x;
     const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
     moments_strip<false>(reinterpret_cast<const uint32_t *>(base - (sh >> 3)), pitch >> 2, sh, x, y0, y_end, width, height, mom1, mom2,
-                         mom_pitch, currx, need);
+                         mom_pitch, currx);
 }
 
 // The same table from tiles staged in SHARED MEMORY by bulk asynchronous copies (cp.async.bulk + mbarrier, the TMA
@@ -514,8 +474,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 __global__ void __launch_bounds__(MB_COLS) moments_bulk_kernel(const uint8_t *__restrict__ img, int pitch, int width, int height,
                                                                 int4 *__restrict__ mom1, mom2_t *__restrict__ mom2, int mom_pitch,
-                                                                currx_t *__restrict__ currx, int tiles_x, int n_tiles,
-                                                                const unsigned *__restrict__ row_mask) {
+                                                                currx_t *__restrict__ currx, int tiles_x, int n_tiles) {
     __shared__ __align__(16) uint8_t tile[MB_STAGES][MB_TILE_ROWS * MB_ROWB];
     __shared__ __align__(8) uint64_t bar[MB_STAGES];
     const int tx = threadIdx.x;
@@ -543,11 +502,10 @@ __global__ void __launch_bounds__(MB_COLS) moments_bulk_kernel(const uint8_t *__
         const int x0 = (t % tiles_x) * MB_COLS, y0 = (t / tiles_x) * MB_ROWS;
         const int x = x0 + tx;
         const int y_end = min(y0 + MB_ROWS, height - 8);
-        const unsigned long long need = needed_rows(row_mask, y0);
-        if (x <= width - 16 && y0 < y_end && (need << (64 - MB_ROWS))) {  // a tile none of whose rows is read is only waited for
+        if (x <= width - 16 && y0 < y_end) {
             const unsigned sh = (unsigned)(tx & 3) * 8u;
             moments_strip<true>(reinterpret_cast<const uint32_t *>(&tile[s][tx & ~3]), MB_ROWB >> 2, sh, x, y0, y_end, width, height, mom1,
-                                mom2, mom_pitch, currx, need);
+                                mom2, mom_pitch, currx);
         }
         __syncthreads();  // every thread is done reading stage s before it is refilled two passes later
     }
@@ -708,9 +666,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
         total += (counts[c] + 31u) & ~31u;
     }
     unsigned my_evals = 0;
-    // the moments kernel of this update has consumed the row mask: clear it for the next update's emit_pixel
-    if (P.row_mask && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < P.mask_words; i += NCC_THREADS) P.row_mask[i] = 0u;
 
     for (;;) {
         unsigned g = 0;

@@ -293,44 +293,6 @@ def test_cyclic_contexts_are_bit_identical_to_one_context(DF, seq640, blk):
     assert all(tot[k] == cw[k] for k in tot)
 
 
-@pytest.mark.parametrize("name,n_upd", [("remode_640x480", 12), ("kitti_1241x376", 6)])
-def test_row_masked_moment_tables_are_bit_identical(DF, monkeypatch, name, n_upd):
-    """DMF_MOMENTS_MASK=1 (default for contexts of a split over >= 4 parts): the moments kernel stores only the table rows
-    that the update's searches can read.  Lateral and forward (radial epipolar lines) motion; whole frame and a 4-part
-    block-cyclic split against the unmasked whole-frame context, maps and work counters."""
-    seq = make_sequence(name, n_frames=n_upd + 1)
-    frames = [seq.render_host(i) for i in range(seq.n_frames)]
-    p = seq.params
-    h, w = seq.shape
-    monkeypatch.setenv("DMF_MOMENTS_MASK", "0")
-    plain = DF(p)
-    monkeypatch.setenv("DMF_MOMENTS_MASK", "1")
-    masked = DF(p)
-    monkeypatch.delenv("DMF_MOMENTS_MASK")
-    parts = [DF(p, cyclic=(8, 4, r)) for r in range(4)]  # masked by default
-    for f in [plain, masked] + parts:
-        f.set_reference(frames[0])
-        f.fill_state(3.0, 3.0)
-    for i in range(1, seq.n_frames):
-        for f in [plain, masked] + parts:
-            f.update(frames[i], seq.T_C_R(i))
-    d0, c0 = plain.download_state()
-    d1, c1 = masked.download_state()
-    d2, c2 = np.full((h, w), 3.0), np.full((h, w), 3.0)
-    tot = {"active": 0, "ncc_evals": 0, "accepted": 0, "interior": 0}
-    for f in parts:
-        f.download_state(d2, c2)
-        for k in tot:
-            tot[k] += f.counters()[k]
-    cp, cm = plain.counters(), masked.counters()
-    for f in [plain, masked] + parts:
-        f.close()
-    assert cp["ncc_evals"] > 0
-    assert np.array_equal(d0, d1, equal_nan=True) and np.array_equal(c0, c1, equal_nan=True)
-    assert np.array_equal(d0, d2, equal_nan=True) and np.array_equal(c0, c2, equal_nan=True)
-    assert all(cp[k] == cm[k] == tot[k] for k in tot)
-
-
 def test_full_size_properties_hd(DF):
     """BASELINE.json config 4 size (1920x1080): determinism (two runs bit-identical), exact parity on a row
     subset against the oracle, work counters consistent."""
