@@ -72,6 +72,23 @@ def test_remode640_sequence(DF, seq640):
     assert (d[:p.border] == 3.0).all() and (d[:, :p.border] == 3.0).all() and (c[-p.border:] == 3.0).all()
 
 
+@pytest.mark.parametrize("w,h,border", [(64, 64, 20), (97, 75, 13), (130, 67, 13), (333, 201, 20)])
+def test_ragged_sizes_and_minimum_border(DF, w, h, border):
+    """Smallest frame, odd widths / heights (partial 32x8 tiles, generic-width ncc_kernel, per-column moments kernel) and
+    the smallest border the tables support (13: samples read block positions up to x = width-16, y = height-9)."""
+    seq = make_sequence("custom", n_frames=5, width=w, height=h, kind="lateral")
+    seq.params.border = border
+    frames = [seq.render_host(i) for i in range(seq.n_frames)]
+    d, c, d_ref, c_ref, worst, ys, cnt, oc = run_pair(DF, seq, frames, 4)
+    p = seq.params
+    assert oc["ncc_evals"] > 0 and oc["interior"] == 4 * (w - 2 * border) * (h - 2 * border)
+    assert depth_agreement(p, d, d_ref, rtol=1e-6) > 0.999
+    assert worst <= MAX_DECISION_MISMATCH and class_mismatch(p, c, c_ref) <= MAX_DECISION_MISMATCH
+    for k in ("interior", "active", "ncc_evals", "accepted"):
+        assert abs(cnt[k] - oc[k]) <= 1e-3 * max(oc[k], 1), (k, cnt[k], oc[k])
+    assert (d[:border] == 3.0).all() and (d[:, :border] == 3.0).all() and (c[-border:] == 3.0).all() and (c[:, -border:] == 3.0).all()
+
+
 def test_golden_sequence_from_compiled_reference(DF):
     """GPU vs the fixture produced by the compiled reference TU (tests/golden/make_golden.py)."""
     g = np.load(G / "remode640_ref_update.npz")
