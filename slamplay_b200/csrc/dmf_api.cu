@@ -75,9 +75,6 @@ struct dmf_ctx_impl {
     std::string trace_path;
     int mom_repeat = 1;                        // DMF_MOMENTS_REPEAT (diagnostic): launches per update; the extra time per update is the exposed cost of one
     int mom_grid = 296;                        // persistent CTAs of moments_bulk_kernel (DMF_MOMENTS_CTAS_PER_SM x SMs)
-    void (*ncc_line_fn)(dmf::KParams) = nullptr;  // ncc_line_kernel (half-warp per unit) for sparse updates
-    int ncc_line_grid = 0;
-    int line_permille = -1;                    // DMF_NCC_LINE_PERMILLE: ncc_line_kernel takes updates with fewer searching pixels than this share
     void (*ncc_fn)(dmf::KParams) = nullptr;    // ncc_kernel specialised for the image width (BASELINE.json's resolutions) or generic
     // optional per-kernel timing (dmf_set_timing): 5 events per update bracket the 4 timing slots
     bool timing_on = false;
@@ -146,7 +143,6 @@ void fill_kparams(dmf_ctx_impl *c, dmf::KParams &K, unsigned long long u) {
     const dmf_params &p = c->prm;
     const int b = (int)(u & 1);  // parity of update u: slot buffers and moment-table buffer
     K.width = p.width; K.height = p.height; K.border = p.border;
-    K.line_permille = c->line_permille;
     K.row0 = c->row0; K.blk = c->blk; K.cyc = c->cyc; K.ph = c->ph; K.n_rows = c->n_rows; K.rev_round = c->rev_round;
     K.inverse_depth = p.inverse_depth; K.write_flags = c->flags_on ? 1 : 0;
     K.ncc_thresh = p.ncc_thresh;
@@ -280,7 +276,6 @@ int launch_update(dmf_ctx_impl *c, const uint8_t *d_curr, int curr_pitch, const 
         if (ev[2]) CU(cudaEventRecord(ev[2], c->stream));
         if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 4);
         c->ncc_fn<<<c->ncc_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);
-        if (c->line_permille >= 0) c->ncc_line_fn<<<c->ncc_line_grid, dmf::NCC_THREADS, 0, c->stream>>>(K);  // one of the two returns at once
         if (tr) stamp_kernel<<<1, 1, 0, c->stream>>>(tr + 5);
         CU(cudaEventRecord(c->ev_tab_free[b], c->stream));
         if (ev[3]) CU(cudaEventRecord(ev[3], c->stream));
@@ -506,14 +501,6 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             case 3840: c->ncc_fn = sb ? dmf::ncc_kernel<3840, true> : dmf::ncc_kernel<3840, false>; break;
             default: c->ncc_fn = sb ? dmf::ncc_kernel<0, true> : dmf::ncc_kernel<0, false>; break;
         }
-        switch (params->width) {
-            case 640: c->ncc_line_fn = dmf::ncc_line_kernel<640>; break;
-            case 1241: c->ncc_line_fn = dmf::ncc_line_kernel<1241>; break;
-            case 1920: c->ncc_line_fn = dmf::ncc_line_kernel<1920>; break;
-            case 3840: c->ncc_line_fn = dmf::ncc_line_kernel<3840>; break;
-            default: c->ncc_line_fn = dmf::ncc_line_kernel<0>; break;
-        }
-        if (const char *lf = std::getenv("DMF_NCC_LINE_PERMILLE")) c->line_permille = std::atoi(lf);
         {
             // Kernels that are to share an SM must agree on its L1 / shared-memory split: ncc_kernel uses no shared memory,
             // moments_bulk_kernel stages its tiles there; with different carve-outs the second kernel's CTAs wait until
@@ -522,15 +509,12 @@ static int create_common(const dmf_params *params, int device, int row_begin, in
             const int carve = cv ? std::atoi(cv) : 14;
             if (carve >= 0) {
                 CUX(cudaFuncSetAttribute(c->ncc_fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-                CUX(cudaFuncSetAttribute(c->ncc_line_fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
                 CUX(cudaFuncSetAttribute(dmf::moments_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             }
         }
         CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ncc_fn, dmf::NCC_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         c->ncc_grid = prop.multiProcessorCount * per_sm;  // persistent CTAs: one resident wave
-        CUX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->ncc_line_fn, dmf::NCC_THREADS, 0));
-        c->ncc_line_grid = prop.multiProcessorCount * (per_sm < 1 ? 1 : per_sm);
         {
             const char *mm = std::getenv("DMF_MOMENTS"), *mc = std::getenv("DMF_MOMENTS_CTAS_PER_SM");
             // moments_bulk_kernel (tiles staged by bulk asynchronous copies) for frames with enough tiles to feed every SM

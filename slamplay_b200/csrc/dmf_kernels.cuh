@@ -113,10 +113,6 @@ struct KParams {
     // (block-cyclic: blocks of `blk` rows dealt to `cyc` contexts in boustrophedon order, so a load that
     //  varies linearly down the image splits evenly; this context is number `ph`;
     //  a contiguous band is blk = n_rows, cyc = 1, ph = 0).
-    // Both NCC kernels are launched every update; each looks at the unit counts and returns at once if the update is
-    // the other's: ncc_line_kernel takes it when fewer than line_permille / 1000 of the context's pixels search
-    // (tail units ~ searching pixels).  < 0: ncc_kernel always.
-    int line_permille;
     int row0, blk, cyc, ph, n_rows;
     int rev_round;  // index of the incomplete last round (dealt from the highest context down whatever its parity), or -1
     int wi;                  // width - 2*border
@@ -551,13 +547,6 @@ __device__ __forceinline__ double ncc_combine(const SampleInts &s, double den1, 
 }
 
 // K2b: NCC over the work units.
-__device__ __forceinline__ bool sparse_update(const KParams &P, const unsigned (&counts)[CHUNK + 1]) {
-    if (P.line_permille < 0) return false;
-    unsigned tails = 0;
-#pragma unroll
-    for (int c = 1; c < CHUNK; ++c) tails += counts[c];
-    return (unsigned long long)tails * 1000ull < (unsigned long long)P.line_permille * (unsigned long long)(P.wi * P.n_rows);
-}
 
 // One sample's memory operands: the 8 rows of the 8x8 block (one aligned 64-bit word each, from the expanded frame)
 // and 5 vectors of the moment table.  All loads are issued before the first use (memory-level parallelism).
@@ -677,7 +666,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
         total += (counts[c] + 31u) & ~31u;
     }
     unsigned my_evals = 0;
-    if (sparse_update(P, counts)) return;  // ncc_line_kernel's update
 
     for (;;) {
         unsigned g = 0;
@@ -753,94 +741,6 @@ __global__ void __launch_bounds__(NCC_THREADS, SHIFT_BLOCK ? DMF_NCC_MIN_BLOCKS 
                 if (v > best_v) { best_v = v; best_k = k0 + j; }  // first strict maximum ref:438-441
             }
             if (best_k >= 0) atomicMax(&P.best[slot], ncc_key(best_v, best_k));
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
-    if (lane == 0 && my_evals) atomicAdd(&P.counters[1], (unsigned long long)my_evals);
-}
-
-// ncc_line_kernel: the same work units with the OTHER mapping — half a warp per unit, lane = sample.  For updates in
-// which few pixels are still active (late in a sequence: 5 % of the pixels, the ones that do not converge, with long
-// searches).  There the 32 lanes of an ncc_kernel warp hold pixels scattered over one or two tiles; every lane walks its
-// own cache lines (measured at 4K, update 300: 6.2 L1 tags per load request instead of 2.4, 5.9 instead of 2.0 wavefronts
-// per NCC, L1 hit rate 40 %, L1/TEX at 88 % of its peak: 25 instead of 95 G NCC/s).  Here the 16 lanes of a half-warp
-// hold CONSECUTIVE samples of one search, 0.7 px apart on one line: their block rows and moment entries share cache
-// lines whatever the neighbours do; record and reference patch are broadcast loads.  The price: no reuse of the
-// integer position between consecutive samples, the reference patch is fetched per sample, and units shorter than 16
-// leave lanes idle — which is why the dense phase keeps ncc_kernel.  Same arithmetic per sample (load_raw / reduce_raw /
-// ncc_combine), same accumulated l (k0 + lane additions), first strict maximum by (value, index) across the half-warp.
-template <int WIDTH>
-__global__ void __launch_bounds__(NCC_THREADS, DMF_NCC_MIN_BLOCKS + 1) ncc_line_kernel(const __grid_constant__ KParams P) {
-    const int lane = threadIdx.x & 31, sub_lane = lane & 15, hw = lane >> 4;
-    unsigned counts[CHUNK + 1];
-    unsigned total = 0;
-#pragma unroll
-    for (int c = CHUNK; c >= 1; --c) {
-        counts[c] = P.ctrl->count[c];
-        total += (counts[c] + 31u) & ~31u;
-    }
-    unsigned my_evals = 0;
-    if (!sparse_update(P, counts)) return;  // ncc_kernel's update
-    const unsigned W = WIDTH ? (unsigned)WIDTH : (unsigned)P.width;
-    for (;;) {
-        unsigned g = 0;
-        if (lane == 0) g = atomicAdd(&P.ctrl->cursor, (unsigned)GRAB);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= total) break;
-        unsigned units[GRAB / 32];
-        int lens[GRAB / 32];
-        fetch_units(P, counts, total, g, lane, units, lens);
-#pragma unroll 1
-        for (int r = 0; r < GRAB / 2; ++r) {  // two units per round: entries 2r and 2r+1 of the grab
-            const int e = 2 * r + hw;         // < GRAB
-            const unsigned unit = __shfl_sync(0xffffffffu, (e < 32) ? units[0] : units[GRAB / 32 - 1], e & 31);
-            const int L = __shfl_sync(0xffffffffu, (e < 32) ? lens[0] : lens[GRAB / 32 - 1], e & 31);
-            const bool mine = sub_lane < L;   // L == 0: no unit in this entry
-            if (!__any_sync(0xffffffffu, mine)) continue;
-            double v = -1.0;                  // ref:430
-            int k = 0x7fffffff;
-            unsigned slot = 0;
-            if (mine) {
-                slot = unit >> CHUNK_BITS;
-                const int k0 = (int)(unit & ((1u << CHUNK_BITS) - 1u)) * CHUNK;
-                const PixelRec *rec = P.rec + slot;
-                const double2 pm = rec->pm, dir = rec->dir;
-                const int4 hv = *reinterpret_cast<const int4 *>(&rec->half);
-                const int4 xy = rec->xy;
-                const double half = __hiloint2double(hv.y, hv.x);
-                // l of sample k0 + sub_lane: that many additions of the step, as the reference accumulates them (ref:432)
-                const double l = dmf_geom::sample_l_acc(half, P.step, k0 + sub_lane);
-                const double cx = __dadd_rn(pm.x, __dmul_rn(l, dir.x));  // ref:433, unfused like the reference build
-                const double cy = __dadd_rn(pm.y, __dmul_rn(l, dir.y));
-                if (cx >= P.bd && cy >= P.bd && cx + P.bd < P.wd && cy + P.bd <= P.hd) {  // inside() ref:222-224
-                    uint32_t R0lo[7], R0hi[7];
-                    const uint2 *rp = P.refx + (unsigned)(xy.y - 3) * W + (unsigned)xy.x;
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const uint2 q = __ldg(rp + (size_t)j * W);
-                        R0lo[j] = q.x; R0hi[j] = q.y;
-                    }
-                    int ix, iy;
-                    double fx, fy;
-                    split_coord(cx, ix, fx);
-                    split_coord(cy, iy, fy);
-                    RawSample raw;
-                    load_raw<WIDTH>(P, ix, iy, raw);
-                    const SampleInts si = reduce_raw<true>(raw, R0lo, R0hi, R0lo, R0hi, hv.z);
-                    const double val = ncc_combine(si, (double)hv.w, fx, fy);
-                    ++my_evals;
-                    if (val > -1.0) { v = val; k = k0 + sub_lane; }  // candidates of `best_ncc < curr_ncc` (ref:438), NaN never
-                }
-            }
-            // first strict maximum of the unit (ref:438-441): largest value, smallest index among equals
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                const double ov = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o), __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
-                const int ok = __shfl_xor_sync(0xffffffffu, k, o);
-                if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
-            }
-            if (mine && sub_lane == 0 && k != 0x7fffffff) atomicMax(&P.best[slot], ncc_key(v, k));
         }
     }
 #pragma unroll
