@@ -745,7 +745,7 @@ def cpu_baseline_and_parity(args, seq, frames, sf, torch, target_ncc: float) -> 
         sample = (f"all {len(rows)} interior rows x all {seq.n_frames - 1} updates; compiled reference translation unit (oracle/_ref), "
                   f"its own OpenMP loop (ref:356), {cores} threads")
     else:
-        rows, stride = cpu_rows_sample(p, args.cpu_rows or max(16, default_cpu_rows(seq, target_ncc * cores)))
+        rows, stride = cpu_rows_sample(p, args.cpu_rows or max(32, default_cpu_rows(seq, target_ncc * cores)))
         sample = (f"{len(rows)} of {h - 2 * p.border} interior rows (every {stride}th from y={rows[0]}) x all {seq.n_frames - 1} "
                   f"updates; oracle port with the reference's per-NCC heap allocations, {cores} OpenMP threads")
     spec = (rows[0], stride, len(rows))
