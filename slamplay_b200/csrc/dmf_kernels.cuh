@@ -56,7 +56,10 @@
 namespace dmf {
 
 constexpr int TILE_W = 32;
-constexpr int TILE_H = 8;
+#ifndef DMF_TILE_H
+#define DMF_TILE_H 8
+#endif
+constexpr int TILE_H = DMF_TILE_H;
 constexpr int TILE_PIX = TILE_W * TILE_H;
 #ifndef DMF_CHUNK
 #define DMF_CHUNK 16
