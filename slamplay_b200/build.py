@@ -63,11 +63,13 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     build.mkdir(exist_ok=True)
     ccbin = ["-ccbin", _host_cxx()]
     extra = os.environ.get("DMF_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DDMF_NCC_MIN_BLOCKS=3
-    out1 = _run([nvcc, *NVCC_FLAGS, *extra, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")], build / "dmf_api.ptxas.log")
+    # -fopenmp: the host-side row copies / compares of dmf_update_strict (16*W*H bytes per call) run on a few threads
+    out1 = _run([nvcc, *NVCC_FLAGS, "-Xcompiler", "-fopenmp", *extra, *ccbin, "-c", str(CSRC / "dmf_api.cu"), "-o", str(build / "dmf_api.o")],
+                build / "dmf_api.ptxas.log")
     _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "microbench.cu"), "-o", str(build / "microbench.o")], build / "microbench.ptxas.log")
     _run([nvcc, *NVCC_FLAGS, *ccbin, "-c", str(CSRC / "frame_ring.cu"), "-o", str(build / "frame_ring.o")], build / "frame_ring.ptxas.log")
     _run([nvcc, "-shared", *ccbin, "-o", str(target), str(build / "dmf_api.o"), str(build / "microbench.o"),
-          str(build / "frame_ring.o"), "-lcudart", "-lrt"])
+          str(build / "frame_ring.o"), "-lcudart", "-lrt", "-lgomp"])
     if verbose:
         print(out1)
     return target

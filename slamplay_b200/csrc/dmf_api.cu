@@ -765,6 +765,9 @@ static unsigned long long image_hash(const uint8_t *img, size_t step, int width,
     return (h[0] ^ (h[1] << 1) ^ (h[2] << 2) ^ (h[3] << 3)) + (unsigned long long)width * 1315423911ull + (unsigned long long)height;
 }
 
+#ifndef STRICT_HOST_THREADS
+#define STRICT_HOST_THREADS 4
+#endif
 int dmf_update_strict(dmf_ctx *c, const uint8_t *ref_host, size_t ref_step, const uint8_t *curr_host, size_t curr_step,
                       const double q[4], const double t[3], double *depth, size_t depth_step, double *cov2, size_t cov2_step) {
     if (!c || !ref_host || !curr_host || !q || !t || !depth || !cov2) return fail(c, DMF_ERR_INVALID, "dmf_update_strict: NULL argument");
@@ -786,13 +789,18 @@ int dmf_update_strict(dmf_ctx *c, const uint8_t *ref_host, size_t ref_step, cons
     //    rows that still equal what the previous call returned are already in HBM
     for (int b = 0; b < 2; ++b)
         if (!c->h_shadow[b]) { CU(cudaMallocHost(&c->h_shadow[b], rowb * H)); c->shadow_valid = false; }
-    bool same = c->shadow_valid;
-    if (same)
-        for (int y = 0; y < H && same; ++y)
-            same = std::memcmp((const char *)depth + (size_t)y * depth_step, c->h_shadow[0] + (size_t)y * W, rowb) == 0 &&
+    // (the row loops of this function run on a few host threads: they move 16*W*H bytes per call and were, single-threaded,
+    //  the larger half of a 640x480 call)
+    int same = c->shadow_valid ? 1 : 0;
+    if (same) {
+#pragma omp parallel for num_threads(STRICT_HOST_THREADS) reduction(&& : same) schedule(static)
+        for (int y = 0; y < H; ++y)
+            same = same && std::memcmp((const char *)depth + (size_t)y * depth_step, c->h_shadow[0] + (size_t)y * W, rowb) == 0 &&
                    std::memcmp((const char *)cov2 + (size_t)y * cov2_step, c->h_shadow[1] + (size_t)y * W, rowb) == 0;
+    }
     if (!same) {
         { int rc_ = flush_pending(c); if (rc_) return rc_; }
+#pragma omp parallel for num_threads(STRICT_HOST_THREADS) schedule(static)
         for (int y = 0; y < H; ++y) {
             std::memcpy(c->h_shadow[0] + (size_t)y * W, (const char *)depth + (size_t)y * depth_step, rowb);
             std::memcpy(c->h_shadow[1] + (size_t)y * W, (const char *)cov2 + (size_t)y * cov2_step, rowb);
@@ -809,8 +817,10 @@ int dmf_update_strict(dmf_ctx *c, const uint8_t *ref_host, size_t ref_step, cons
     CU(cudaEventRecord(c->ev_frame, c->stream));
     CU(cudaMemcpyAsync(c->h_shadow[1], c->d_cov2, rowb * H, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventSynchronize(c->ev_frame));
+#pragma omp parallel for num_threads(STRICT_HOST_THREADS) schedule(static)
     for (int y = 0; y < H; ++y) std::memcpy((char *)depth + (size_t)y * depth_step, c->h_shadow[0] + (size_t)y * W, rowb);
     CU(cudaStreamSynchronize(c->stream));
+#pragma omp parallel for num_threads(STRICT_HOST_THREADS) schedule(static)
     for (int y = 0; y < H; ++y) std::memcpy((char *)cov2 + (size_t)y * cov2_step, c->h_shadow[1] + (size_t)y * W, rowb);
     c->shadow_valid = true;
     return DMF_OK;
